@@ -1,0 +1,219 @@
+/*
+ * plo_c_api.h — C ABI of the B200-native IMLS-ICP scan-to-map registration path.
+ *
+ * This is the drop-in boundary: plain C types, opaque handle, no
+ * exceptions, no torch types.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference root).  The reference has no FFI today
+ * (string dispatch on config.json inside src/laser_odometry.cpp:487-568,606); the
+ * binding a maintainer would add is shown in INTEGRATION.md, and
+ * include/plo/imls_icp_cuda.h is the C++ adapter that mirrors class IMLSICPMatcher.
+ *
+ * Conventions
+ *   - 4x4 transforms are row-major double[16].
+ *   - Point records: `stride` bytes per point, float32 xyz at byte 0, float32 normal
+ *     at byte 16 (pcl::PointXYZINormal = PointType, include/common.h:17; stride 48).
+ *   - Points whose x/y/z is non-finite are stripped on upload, order preserved
+ *     (RemoveNANandINFData, src/imls_icp.cpp:58-72); every index this API returns
+ *     refers to the stripped cloud, exactly like the reference after its erase().
+ *   - All functions return PLO_OK (0) or a negative plo_error; plo_last_error() gives
+ *     the message.  A context is bound to one device and one stream, and is not
+ *     thread-safe (the reference's matcher is not re-entrant either); use one context
+ *     per host thread.  All device memory is owned by the context.
+ *   - There is no CPU fallback: without a CUDA device plo_create fails.
+ */
+#ifndef PLO_C_API_H
+#define PLO_C_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PLO_API __attribute__((visibility("default")))
+#else
+#define PLO_API
+#endif
+
+typedef struct plo_ctx plo_ctx;
+
+typedef enum plo_error {
+  PLO_OK = 0,
+  PLO_ERR_INVALID_ARG = -1,
+  PLO_ERR_CUDA = -2,
+  PLO_ERR_NO_DEVICE = -3,
+  PLO_ERR_UNSUPPORTED = -4,
+  PLO_ERR_STATE = -5
+} plo_error;
+
+/* per-source-point outcome; 1..6 are the six drop counters of
+ * src/imls_icp.cpp:506-511,736-744 in their order of declaration */
+typedef enum plo_point_status {
+  PLO_PT_OK = 0,
+  PLO_PT_NO_NORMAL = 1,          /* :612-617  no 1-NN within r            */
+  PLO_PT_TOO_FAR = 2,            /* :620-625  d2(1-NN) > h*h              */
+  PLO_PT_INVALID_NORMAL = 3,     /* :673-679                              */
+  PLO_PT_NORMAL_CONSTRAINT = 4,  /* :681-692                              */
+  PLO_PT_MLS_FAIL = 5,           /* :696-701  (< 3 usable IMLS neighbours) */
+  PLO_PT_NAN_INF_HEIGHT = 6      /* :703-717                              */
+} plo_point_status;
+
+/* outcome of plo_register: how the loop of src/laser_odometry.cpp:524-647 ended */
+typedef enum plo_reg_status {
+  PLO_REG_CONVERGED = 1,     /* :643-646 */
+  PLO_REG_MAX_ITERS = 2,     /* :524 loop bound */
+  PLO_REG_TOO_FEW_PAIRS = 3, /* :570-576 */
+  PLO_REG_SOLVE_FAILED = 4   /* :611-616 (no pivot at all: every pair had a zero row) */
+} plo_reg_status;
+
+typedef enum plo_weight_mode {
+  PLO_W_UNIT = 0,     /* plain point-to-plane LS (weights = 1)                         */
+  PLO_W_HUBER_EXP = 1 /* RANSAC-final weights of src/solver.cpp:334-364 at T_best = I  */
+} plo_weight_mode;
+
+/* IMLSICPMatcher::setParameters (src/imls_icp.cpp:146-168; fields
+ * include/imls_icp.h:115-146) + the driver-loop keys of config.json.  The tensor-voting
+ * and projected-distance switches are not represented: those branches are out of scope
+ *  and requesting them through the adapter is PLO_ERR_UNSUPPORTED. */
+typedef struct plo_params {
+  int32_t iterations;              /* solve_method.iterations                         30 */
+  double h;                        /* IMLS.h: 1-NN gate (d2 <= h*h)                    1 */
+  double r;                        /* IMLS.r: search radius                            3 */
+  double r_normal;                 /* get_normals.r_normal                             1 */
+  int32_t is_get_normals;          /* get_normals.enabled: 1 = use delivered normals   1 */
+  int32_t search_number_normal;    /* get_normals.search_number_normal (<= 32)        10 */
+  int32_t search_number;           /* "IMLS function".search_number (<= 32)           20 */
+  int32_t normal_angle_constraint; /* normal_angle_constraint.enabled                  1 */
+  double angle_diff_threshold;     /* normal_angle_constraint.angle_diff_threshold    30 */
+  int32_t transform_normal;        /* laser_odometry.transform_normal                  0 */
+  int32_t correspond_number;       /* matching_method.correspond_number                6 */
+  double delta_dist_threshold;     /* solve_method.delta_dist_threshold            1e-3 */
+  double delta_angle_threshold;    /* solve_method.delta_angle_threshold   1.745353e-4 */
+  int32_t weight_mode;             /* plo_weight_mode                                  0 */
+  double ransac_distance_threshold;/* RANSAC.distance_threshold (PLO_W_HUBER_EXP)    0.8 */
+  double huber_threshold;          /* RANSAC.huber_threshold    (PLO_W_HUBER_EXP)  0.648 */
+} plo_params;
+
+typedef struct plo_proj_stats {
+  int64_t n_source;   /* source points after the non-finite strip                       */
+  int64_t n_pairs;    /* surviving correspondences ("USED POINTS FINAL")                */
+  int64_t dropped[6]; /* the six counters of src/imls_icp.cpp:736-744                   */
+} plo_proj_stats;
+
+typedef struct plo_reg_stats {
+  int32_t status;      /* plo_reg_status                                                */
+  int32_t iters;       /* solves performed                                              */
+  int64_t pairs;       /* pairs of the last projection                                  */
+  double rms;          /* sqrt(mean(b_i^2)) of the last projection, b_i = n.(y - x)     */
+  int64_t dropped[6];  /* counters of the last projection                                */
+  double delta_dist;   /* |t| of the last delta  (src/laser_odometry.cpp:628-632)       */
+  double delta_angle;  /* angle of the last delta (:636-638)                            */
+  int32_t rank;        /* pivots used by the last 6x6 solve                             */
+  int32_t reserved;
+} plo_reg_stats;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+PLO_API int plo_create(int device, plo_ctx** out);
+PLO_API void plo_destroy(plo_ctx* ctx);
+/* message of the last failing call on ctx (ctx may be NULL: last plo_create failure) */
+PLO_API const char* plo_last_error(const plo_ctx* ctx);
+PLO_API int plo_version(void);
+/* run everything on a caller-owned CUDA stream (cudaStream_t passed as void*) */
+PLO_API int plo_set_stream(plo_ctx* ctx, void* cuda_stream);
+PLO_API int plo_synchronize(plo_ctx* ctx);
+
+/* ---- parameters: IMLSICPMatcher::setParameters, src/imls_icp.cpp:146-168 --------- */
+PLO_API void plo_default_params(plo_params* p);
+PLO_API int plo_set_params(plo_ctx* ctx, const plo_params* p);
+
+/* ---- clouds ----------------------------------------------------------------------
+ * plo_set_target  == IMLSICPMatcher::setTargetPointCloud, src/imls_icp.cpp:80-103:
+ *   strips non-finite points, builds the spatial index in HBM (replaces
+ *   Nabo::NNSearchD::createKDTreeLinearHeap, :101).
+ * plo_set_source  == IMLSICPMatcher::setSourcePointCloud, src/imls_icp.cpp:74-78.
+ * The *_device variants take pointers to records already resident in device memory
+ * (same layout); the records are consumed before the call's work completes on the
+ * context's stream, the caller keeps ownership. */
+PLO_API int plo_set_target(plo_ctx* ctx, const void* host_pts, int64_t n, int32_t stride_bytes);
+PLO_API int plo_set_source(plo_ctx* ctx, const void* host_pts, int64_t n, int32_t stride_bytes);
+PLO_API int plo_set_target_device(plo_ctx* ctx, const void* dev_pts, int64_t n, int32_t stride_bytes);
+PLO_API int plo_set_source_device(plo_ctx* ctx, const void* dev_pts, int64_t n, int32_t stride_bytes);
+/* sizes after the strip (synchronises the stream) */
+PLO_API int64_t plo_target_size(plo_ctx* ctx);
+PLO_API int64_t plo_source_size(plo_ctx* ctx);
+
+/* ---- one matcher pass -------------------------------------------------------------
+ * plo_project == the per-iteration source transform of src/laser_odometry.cpp:527-549
+ * followed by IMLSICPMatcher::ProjSourcePtToSurface (src/imls_icp.cpp:496-745) with
+ * ImplicitMLSFunction (:301-483) fused in.  T = current rPose.  Results stay on the
+ * device; stats may be NULL (no synchronisation then).  With `hooks` != 0 the per-query
+ * parity data of plo_get_neighbors / plo_get_query_results is recorded as well. */
+PLO_API int plo_project(plo_ctx* ctx, const double T[16], int32_t hooks, plo_proj_stats* stats);
+/* correspondences of the last plo_project, compacted in source order — the contents of
+ * in_cloud / out_cloud after ProjSourcePtToSurface returns (src/imls_icp.cpp:719-731).
+ * float32 triplets; src_idx = index of each pair's point in the stripped source
+ * (replaces the in-place erase).  Any output pointer may be NULL. */
+PLO_API int plo_get_pairs(plo_ctx* ctx, float* src_xyz, float* ref_xyz, float* ref_n,
+                          int32_t* src_idx, int64_t cap, int64_t* n);
+/* parity hooks (need hooks != 0 in the last plo_project): k = search_number.
+ * nn_idx[M*k] / nn_d2[M*k]: the knn of src/imls_icp.cpp:372-375 (-1 / +inf padded);
+ * nn1_idx[M] / nn1_d2[M]: the 1-NN of :601-609.  Any pointer may be NULL. */
+PLO_API int plo_get_neighbors(plo_ctx* ctx, int32_t* nn_idx, double* nn_d2,
+                              int32_t* nn1_idx, double* nn1_d2);
+/* status[M] (plo_point_status), height[M] = I(x) of :480 (NaN where not computed) */
+PLO_API int plo_get_query_results(plo_ctx* ctx, int32_t* status, double* height);
+/* normals the matcher uses for the target, n x 3 doubles in stripped-cloud order:
+ * the delivered ones, or ComputeNormal (src/imls_icp.cpp:753-794) when
+ * is_get_normals == 0 */
+PLO_API int plo_get_target_normals(plo_ctx* ctx, double* out);
+
+/* ---- solver -----------------------------------------------------------------------
+ * plo_solve_wls == SolveMotionEstimationProblemWeightedLS (src/solver.cpp:168-220,
+ * include/solver.h:92-98) on the device-resident pairs of the last plo_project with the
+ * context's weight_mode.  delta = deltaTrans (row-major).  Returns PLO_OK also when the
+ * system is rank-deficient (the reference always returns true); *rank (nullable) tells. */
+PLO_API int plo_solve_wls(plo_ctx* ctx, double delta[16], int32_t* rank);
+/* same solver, reference-shaped inputs: host arrays of n x 3 doubles + n weights
+ * (NULL = unit) — the argument list of SolveMotionEstimationProblemWeightedLS */
+PLO_API int plo_solve_wls_host(plo_ctx* ctx, const double* src, const double* ref,
+                               const double* nrm, const double* w, int64_t n,
+                               double delta[16], int32_t* rank);
+/* parity hook: the reduced normal equations of the last solve: H (21 upper-triangular
+ * entries, row-major), g (6), sum of weights, sum w*b*b, pair count */
+PLO_API int plo_get_normal_equations(plo_ctx* ctx, double H21[21], double g6[6],
+                                     double* sw, double* swbb, int64_t* count);
+
+/* ---- resident registration loop ---------------------------------------------------
+ * plo_register == the ICP loop of src/laser_odometry.cpp:484-485,524-647 (and the shape
+ * of IMLSICPMatcher::Match, src/imls_icp.cpp:804-919): project -> reduce -> 6x6 solve ->
+ * rPose = delta * rPose -> convergence test, all on the device, one host read-back at
+ * the end.  T0 = initial rPose (the reference uses identity; NULL = identity). */
+PLO_API int plo_register(plo_ctx* ctx, const double T0[16], double T[16], plo_reg_stats* stats);
+
+/* ---- batched mode -----------------------------------------------------------------
+ * Registers `count` independent (source, target) pairs one after the other on the
+ * context's stream with a single synchronisation at the end: pair i = host (or device,
+ * if on_device != 0) record arrays sources[i] (n_src[i]) against targets[i] (n_tgt[i]).
+ * T_out[16*count], stats_out[count] (nullable).  This is the unit that is sharded
+ * across GPUs (one context per GPU). */
+PLO_API int plo_register_batch(plo_ctx* ctx, int32_t count,
+                               const void* const* sources, const int64_t* n_src,
+                               const void* const* targets, const int64_t* n_tgt,
+                               int32_t stride_bytes, int32_t on_device,
+                               double* T_out, plo_reg_stats* stats_out);
+
+/* ---- introspection (bench / tests) ------------------------------------------------ */
+/* kernels launched by this context since creation (bench.py's gpu_launches claim) */
+PLO_API int64_t plo_launch_count(const plo_ctx* ctx);
+/* device milliseconds of the last index build / last registration loop, measured with
+ * CUDA events on the context's stream (0 if not measured yet) */
+PLO_API int plo_last_timings(plo_ctx* ctx, float* ms_index_build, float* ms_register);
+/* per-kernel timing of one projection pass for the roofline: runs the projection kernel
+ * `reps` times at the current pose and returns the mean device ms per launch */
+PLO_API int plo_time_project_kernel(plo_ctx* ctx, const double T[16], int32_t reps, float* ms_mean);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLO_C_API_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of csrc/libplo_cuda.so (the C ABI of include/plo/plo_c_api.h).
+
+The library is built in-tree (`make -C csrc`, nvcc, sm_100a only) and loaded from there;
+nothing here falls back to a CPU implementation: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libplo_cuda.so")
+
+PLO_OK = 0
+ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "NO_DEVICE", -4: "UNSUPPORTED", -5: "STATE"}
+POINT_STATUS = ["ok", "no_normal", "too_far", "invalid_normal", "normal_constraint", "mls_fail", "nan_inf_height"]
+REG_STATUS = {1: "CONVERGED", 2: "MAX_ITERS", 3: "TOO_FEW_PAIRS", 4: "SOLVE_FAILED"}
+W_UNIT, W_HUBER_EXP = 0, 1
+
+
+class PloError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"plo error {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class PloParams(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int32), ("h", C.c_double), ("r", C.c_double), ("r_normal", C.c_double),
+        ("is_get_normals", C.c_int32), ("search_number_normal", C.c_int32), ("search_number", C.c_int32),
+        ("normal_angle_constraint", C.c_int32), ("angle_diff_threshold", C.c_double),
+        ("transform_normal", C.c_int32), ("correspond_number", C.c_int32),
+        ("delta_dist_threshold", C.c_double), ("delta_angle_threshold", C.c_double),
+        ("weight_mode", C.c_int32), ("ransac_distance_threshold", C.c_double), ("huber_threshold", C.c_double),
+    ]
+
+
+class PloProjStats(C.Structure):
+    _fields_ = [("n_source", C.c_int64), ("n_pairs", C.c_int64), ("dropped", C.c_int64 * 6)]
+
+
+class PloRegStats(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iters", C.c_int32), ("pairs", C.c_int64), ("rms", C.c_double),
+                ("dropped", C.c_int64 * 6), ("delta_dist", C.c_double), ("delta_angle", C.c_double),
+                ("rank", C.c_int32), ("reserved", C.c_int32)]
+
+
+EXPORTS = [
+    "plo_create", "plo_destroy", "plo_last_error", "plo_version", "plo_set_stream", "plo_synchronize",
+    "plo_default_params", "plo_set_params", "plo_set_target", "plo_set_source", "plo_set_target_device",
+    "plo_set_source_device", "plo_target_size", "plo_source_size", "plo_project", "plo_get_pairs",
+    "plo_get_neighbors", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls",
+    "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
+    "plo_launch_count", "plo_last_timings", "plo_time_project_kernel",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libplo_cuda.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    args = ["make", "-C", CSRC, "-j4"] + (["-B"] if force else [])
+    subprocess.check_call(args, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    L.plo_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.plo_destroy.argtypes = [vp]
+    L.plo_destroy.restype = None
+    L.plo_last_error.argtypes = [vp]
+    L.plo_last_error.restype = C.c_char_p
+    L.plo_set_stream.argtypes = [vp, vp]
+    L.plo_synchronize.argtypes = [vp]
+    L.plo_default_params.argtypes = [C.POINTER(PloParams)]
+    L.plo_default_params.restype = None
+    L.plo_set_params.argtypes = [vp, C.POINTER(PloParams)]
+    for f in (L.plo_set_target, L.plo_set_source, L.plo_set_target_device, L.plo_set_source_device):
+        f.argtypes = [vp, vp, i64, i32]
+    for f in (L.plo_target_size, L.plo_source_size):
+        f.argtypes = [vp]
+        f.restype = i64
+    L.plo_project.argtypes = [vp, vp, i32, C.POINTER(PloProjStats)]
+    L.plo_get_pairs.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.plo_get_neighbors.argtypes = [vp, vp, vp, vp, vp]
+    L.plo_get_query_results.argtypes = [vp, vp, vp]
+    L.plo_get_target_normals.argtypes = [vp, vp]
+    L.plo_solve_wls.argtypes = [vp, vp, C.POINTER(i32)]
+    L.plo_solve_wls_host.argtypes = [vp, vp, vp, vp, vp, i64, vp, C.POINTER(i32)]
+    L.plo_get_normal_equations.argtypes = [vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    L.plo_register.argtypes = [vp, vp, vp, C.POINTER(PloRegStats)]
+    L.plo_register_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, vp, vp]
+    L.plo_launch_count.argtypes = [vp]
+    L.plo_launch_count.restype = i64
+    L.plo_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.plo_time_project_kernel.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def default_params(**over) -> PloParams:
+    p = PloParams()
+    lib().plo_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p

@@ -1,0 +1,224 @@
+"""`Context`: one plo_ctx (one GPU, one stream) with numpy-friendly wrappers.
+
+Inputs may be numpy arrays (host records, copied by the library) or torch CUDA tensors
+(device-resident records, passed by pointer — PyTorch is only the memory/stream plumbing).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PloError, PloParams, PloProjStats, PloRegStats
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _records(x):
+    """-> (pointer, n, stride_bytes, on_device, keepalive)"""
+    if _is_torch_cuda(x):
+        if x.dim() != 2 or x.dtype.itemsize != 4 or x.stride(1) != 1:
+            raise ValueError("device records must be a 2-D float32 tensor with contiguous rows")
+        return C.c_void_p(x.data_ptr()), int(x.shape[0]), int(x.stride(0) * 4) if x.shape[0] > 1 else int(x.shape[1] * 4), True, x
+    if hasattr(x, "is_cuda"):   # torch CPU tensor (possibly pinned): pass its host pointer
+        if x.dim() != 2 or x.dtype.itemsize != 4 or x.stride(1) != 1:
+            raise ValueError("host records must be a 2-D float32 tensor with contiguous rows")
+        return C.c_void_p(x.data_ptr()), int(x.shape[0]), int(x.stride(0) * 4) if x.shape[0] > 1 else int(x.shape[1] * 4), False, x
+    a = np.asarray(x)
+    if a.ndim != 2 or a.dtype != np.float32:
+        raise ValueError("records must be a 2-D float32 array (n, >=7): xyz at floats 0..2, normal at floats 4..6")
+    if a.strides[1] != 4:
+        a = np.ascontiguousarray(a)
+    stride = a.strides[0] if a.shape[0] > 1 else a.shape[1] * 4
+    return _ptr(a), int(a.shape[0]), int(stride), False, a
+
+
+class Context:
+    def __init__(self, device: int = 0, params: PloParams | None = None, stream=None):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        rc = self.L.plo_create(device, C.byref(h))
+        if rc != _lib.PLO_OK:
+            raise PloError(rc, self.L.plo_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.params = params or _lib.default_params()
+        self.set_params(self.params)
+        self._keep = []
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.plo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != _lib.PLO_OK:
+            raise PloError(rc, self.L.plo_last_error(self.h).decode())
+
+    def set_stream(self, stream):
+        """stream: torch.cuda.Stream or a raw cudaStream_t integer"""
+        raw = getattr(stream, "cuda_stream", stream)
+        self._ck(self.L.plo_set_stream(self.h, C.c_void_p(int(raw))))
+        self._stream_keep = stream
+
+    def synchronize(self):
+        self._ck(self.L.plo_synchronize(self.h))
+
+    # -- parameters / clouds ------------------------------------------------------------
+    def set_params(self, params: PloParams):
+        self._ck(self.L.plo_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def set_target(self, rec):
+        p, n, stride, dev, keep = _records(rec)
+        self._keep_t = keep
+        self._ck((self.L.plo_set_target_device if dev else self.L.plo_set_target)(self.h, p, n, stride))
+
+    def set_source(self, rec):
+        p, n, stride, dev, keep = _records(rec)
+        self._keep_s = keep
+        self._ck((self.L.plo_set_source_device if dev else self.L.plo_set_source)(self.h, p, n, stride))
+
+    @property
+    def n_target(self) -> int:
+        return int(self.L.plo_target_size(self.h))
+
+    @property
+    def n_source(self) -> int:
+        return int(self.L.plo_source_size(self.h))
+
+    # -- matcher ------------------------------------------------------------------------
+    def project(self, T=None, hooks: bool = False, stats: bool = True):
+        T = np.ascontiguousarray(np.eye(4) if T is None else T, dtype=np.float64).reshape(16)
+        st = PloProjStats()
+        self._ck(self.L.plo_project(self.h, _ptr(T), 1 if hooks else 0, C.byref(st) if stats else None))
+        if not stats:
+            return None
+        return dict(n_source=int(st.n_source), n_pairs=int(st.n_pairs), counters=np.array(list(st.dropped), np.int64))
+
+    def pairs(self):
+        m = max(self.n_source, 1)
+        sx = np.empty((m, 3), np.float32)
+        rx = np.empty((m, 3), np.float32)
+        rn = np.empty((m, 3), np.float32)
+        si = np.empty(m, np.int32)
+        n = C.c_int64()
+        self._ck(self.L.plo_get_pairs(self.h, _ptr(sx), _ptr(rx), _ptr(rn), _ptr(si), m, C.byref(n)))
+        n = n.value
+        return dict(n=n, src_xyz=sx[:n], ref_xyz=rx[:n], ref_n=rn[:n], src_idx=si[:n])
+
+    def neighbors(self):
+        m, k = self.n_source, self.params.search_number
+        ni = np.empty((m, k), np.int32)
+        nd = np.empty((m, k), np.float64)
+        i1 = np.empty(m, np.int32)
+        d1 = np.empty(m, np.float64)
+        self._ck(self.L.plo_get_neighbors(self.h, _ptr(ni), _ptr(nd), _ptr(i1), _ptr(d1)))
+        return dict(nn_idx=ni, nn_d2=nd, nn1_idx=i1, nn1_d2=d1)
+
+    def query_results(self, heights: bool = True):
+        m = self.n_source
+        st = np.empty(m, np.int32)
+        hg = np.empty(m, np.float64) if heights else None
+        self._ck(self.L.plo_get_query_results(self.h, _ptr(st), _ptr(hg)))
+        return dict(status=st, height=hg)
+
+    def target_normals(self) -> np.ndarray:
+        out = np.empty((max(self.n_target, 0), 3), np.float64)
+        self._ck(self.L.plo_get_target_normals(self.h, _ptr(out)))
+        return out
+
+    # -- solver -------------------------------------------------------------------------
+    def solve_wls(self):
+        d = np.empty(16, np.float64)
+        rank = C.c_int32()
+        self._ck(self.L.plo_solve_wls(self.h, _ptr(d), C.byref(rank)))
+        return d.reshape(4, 4), rank.value
+
+    def solve_wls_host(self, src, ref, nrm, w=None):
+        src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
+        w = None if w is None else np.ascontiguousarray(w, np.float64)
+        d = np.empty(16, np.float64)
+        rank = C.c_int32()
+        self._ck(self.L.plo_solve_wls_host(self.h, _ptr(src), _ptr(ref), _ptr(nrm), _ptr(w), src.shape[0], _ptr(d), C.byref(rank)))
+        return d.reshape(4, 4), rank.value
+
+    def normal_equations(self):
+        H = np.empty(21)
+        g = np.empty(6)
+        sw, sbb, cnt = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self.L.plo_get_normal_equations(self.h, _ptr(H), _ptr(g), C.byref(sw), C.byref(sbb), C.byref(cnt)))
+        return H, g, sw.value, sbb.value, cnt.value
+
+    # -- resident loop ------------------------------------------------------------------
+    def register(self, T0=None):
+        T0a = None if T0 is None else np.ascontiguousarray(T0, np.float64).reshape(16)
+        T = np.empty(16, np.float64)
+        st = PloRegStats()
+        self._ck(self.L.plo_register(self.h, _ptr(T0a), _ptr(T), C.byref(st)))
+        return T.reshape(4, 4), _reg_stats(st)
+
+    def register_batch(self, sources, targets):
+        n = len(sources)
+        assert n == len(targets)
+        recs_s = [_records(s) for s in sources]
+        recs_t = [_records(t) for t in targets]
+        if n == 0:
+            return np.zeros((0, 4, 4)), []
+        dev = recs_s[0][3]
+        stride = recs_s[0][2]
+        for r in recs_s + recs_t:
+            if r[3] != dev or (r[1] > 1 and r[2] != stride):
+                raise ValueError("register_batch: all clouds must live on the same side and share one stride")
+        ps = (C.c_void_p * n)(*[r[0] for r in recs_s])
+        pt = (C.c_void_p * n)(*[r[0] for r in recs_t])
+        ns = (C.c_int64 * n)(*[r[1] for r in recs_s])
+        nt = (C.c_int64 * n)(*[r[1] for r in recs_t])
+        T = np.empty((n, 16), np.float64)
+        st = (PloRegStats * n)()
+        self._ck(self.L.plo_register_batch(self.h, n, ps, ns, pt, nt, stride, 1 if dev else 0, _ptr(T), st))
+        return T.reshape(n, 4, 4), [_reg_stats(s) for s in st]
+
+    # -- introspection ------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.plo_launch_count(self.h))
+
+    def last_timings(self):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.plo_last_timings(self.h, C.byref(a), C.byref(b)))
+        return dict(ms_index_build=a.value, ms_register=b.value)
+
+    def time_project_kernel(self, T=None, reps: int = 10) -> float:
+        T = np.ascontiguousarray(np.eye(4) if T is None else T, dtype=np.float64).reshape(16)
+        ms = C.c_float()
+        self._ck(self.L.plo_time_project_kernel(self.h, _ptr(T), reps, C.byref(ms)))
+        return ms.value
+
+
+def _reg_stats(st: PloRegStats) -> dict:
+    return dict(status=int(st.status), status_name=_lib.REG_STATUS.get(int(st.status), "?"), iters=int(st.iters),
+                pairs=int(st.pairs), rms=float(st.rms), counters=np.array(list(st.dropped), np.int64),
+                delta_dist=float(st.delta_dist), delta_angle=float(st.delta_angle), rank=int(st.rank))

@@ -1,0 +1,443 @@
+// index_build.cu — map index build (replaces IMLSICPMatcher::setTargetPointCloud's
+// Nabo::NNSearchD::createKDTreeLinearHeap, src/imls_icp.cpp:80-103) and source upload
+// (setSourcePointCloud, src/imls_icp.cpp:74-78), including the non-finite strip of
+// RemoveNANandINFData (src/imls_icp.cpp:58-72).
+//
+// Index = "Morton-sorted wide BVH": 48-bit Morton key per point (16 bit/axis over the
+// cloud's bounding cube) -> LSD radix sort (6 x 8 bit, stable) -> leaves of 32
+// consecutive points -> levels of 32 consecutive nodes, one AABB per node.  Everything
+// is sized by the number of uploaded points, so no host synchronisation is needed:
+// non-finite points get the maximal key and +inf coordinates and sink to the tail.
+//
+// Algorithmic bytes per map point: read 24 B (xyz+normal) + write 24 B
+// reordered + 4 B index = 52 B.  Roofline: HBM.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "plo_internal.cuh"
+#include "plo_scan.cuh"
+
+namespace {
+
+constexpr int kSortTile = 4096;   // keys per block in the radix-sort kernels (256 thr x 16)
+constexpr int kSortItems = 16;
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kKeyBits = 48;
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+  unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+  return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+// bbox[0..2] = min (ordered uint), bbox[3..5] = max
+__global__ void k_init_bbox(unsigned* bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+}
+
+// records -> float4 point (w = 1 if xyz finite) + float4 normal; finite count per block;
+// bounding box of the finite points.
+__global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ rec, int stride, int n,
+                                                      float4* __restrict__ praw, float4* __restrict__ nraw,
+                                                      int* __restrict__ blockcnt, unsigned* __restrict__ bbox) {
+  __shared__ int s_cnt[8];
+  const int base = blockIdx.x * kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt = 0;
+  float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+  for (int j = 0; j < kTile / 256; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    if (i < n) {
+      const float* r = reinterpret_cast<const float*>(rec + (size_t)i * stride);
+      const float x = r[0], y = r[1], z = r[2];
+      const float nx = r[4], ny = r[5], nz = r[6];
+      const bool fin = finite3(x, y, z);
+      praw[i] = make_float4(x, y, z, fin ? 1.f : 0.f);
+      nraw[i] = make_float4(nx, ny, nz, 0.f);
+      if (fin) {
+        ++cnt;
+        lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+        hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(PLO_FULL_MASK, cnt, o);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(PLO_FULL_MASK, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(PLO_FULL_MASK, hi[a], o));
+    }
+  }
+  if (lane == 0) {
+    s_cnt[warp] = cnt;
+    if (bbox != nullptr && cnt > 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMin(&bbox[a], f2ord(lo[a]));
+        atomicMax(&bbox[3 + a], f2ord(hi[a]));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_cnt[w];
+    blockcnt[blockIdx.x] = t;
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread16(unsigned v) {
+  unsigned long long x = v & 0xffffu;
+  x = (x | (x << 16)) & 0x0000ff0000ffull;
+  x = (x | (x << 8)) & 0x00f00f00f00full;
+  x = (x | (x << 4)) & 0x0c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x249249249249ull;
+  return x;
+}
+
+// stripped-cloud index of every raw point + Morton key; vals = raw index (iota)
+__global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ praw, int n, const int* __restrict__ blockoff,
+                                              const unsigned* __restrict__ bbox, int* __restrict__ cidx,
+                                              unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const int base = blockIdx.x * kTile;
+  bool fin[kTile / 256];
+  float4 p[kTile / 256];
+#pragma unroll
+  for (int j = 0; j < kTile / 256; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    p[j] = (i < n) ? praw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    fin[j] = p[j].w != 0.f;
+  }
+  int rank[kTile / 256];
+  tile_ranks(fin, rank);
+  const float lox = ord2f(bbox[0]), loy = ord2f(bbox[1]), loz = ord2f(bbox[2]);
+  const float ext = fmaxf(fmaxf(ord2f(bbox[3]) - lox, ord2f(bbox[4]) - loy), ord2f(bbox[5]) - loz);
+  const float scale = (ext > 0.f && isfinite(ext)) ? 65535.f / ext : 0.f;
+  const int off = blockoff[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kTile / 256; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    if (i >= n) continue;
+    unsigned long long key = (1ull << kKeyBits) - 1ull;
+    int ci = -1;
+    if (fin[j]) {
+      ci = off + rank[j];
+      const unsigned qx = min(65535u, (unsigned)fmaxf(0.f, (p[j].x - lox) * scale));
+      const unsigned qy = min(65535u, (unsigned)fmaxf(0.f, (p[j].y - loy) * scale));
+      const unsigned qz = min(65535u, (unsigned)fmaxf(0.f, (p[j].z - loz) * scale));
+      key = spread16(qx) | (spread16(qy) << 1) | (spread16(qz) << 2);
+    }
+    cidx[i] = ci;
+    keys[i] = key;
+    vals[i] = i;
+  }
+}
+
+// order-preserving compaction of the source into float4 point / normal arrays
+__global__ void __launch_bounds__(256) k_compact_source(const float4* __restrict__ praw, const float4* __restrict__ nraw, int n,
+                                                        const int* __restrict__ blockoff, float4* __restrict__ sp,
+                                                        float4* __restrict__ sn) {
+  const int base = blockIdx.x * kTile;
+  bool fin[kTile / 256];
+  float4 p[kTile / 256];
+#pragma unroll
+  for (int j = 0; j < kTile / 256; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    p[j] = (i < n) ? praw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    fin[j] = p[j].w != 0.f;
+  }
+  int rank[kTile / 256];
+  tile_ranks(fin, rank);
+  const int off = blockoff[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kTile / 256; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    if (i < n && fin[j]) {
+      sp[off + rank[j]] = p[j];
+      sn[off + rank[j]] = nraw[i];
+    }
+  }
+}
+
+// ---- LSD radix sort, one 8-bit digit per pass -------------------------------------
+
+__global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __restrict__ keys, int n, int shift,
+                                                   int nb, int* __restrict__ hist) {
+  __shared__ int s_h[kRadix];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int i = base + j * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(unsigned)(keys[i] >> shift) & (kRadix - 1)], 1);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nb + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const unsigned long long* __restrict__ keys_in,
+                                                      const int* __restrict__ vals_in,
+                                                      unsigned long long* __restrict__ keys_out,
+                                                      int* __restrict__ vals_out, int n, int shift, int nb,
+                                                      const int* __restrict__ hist_scanned) {
+  __shared__ int s_w[8][kRadix];   // per-warp running digit counts -> exclusive over warps
+  __shared__ int s_g[kRadix];      // global base of (digit, this block)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < 8 * kRadix; q += 256) (&s_w[0][0])[q] = 0;
+  s_g[threadIdx.x] = hist_scanned[threadIdx.x * nb + blockIdx.x];
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile + warp * (kSortItems * 32);
+  unsigned long long key[kSortItems];
+  int val[kSortItems];
+  int rank[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int i = base + j * 32 + lane;
+    const bool valid = i < n;
+    key[j] = valid ? keys_in[i] : 0ull;
+    val[j] = valid ? vals_in[i] : 0;
+    const unsigned d = valid ? ((unsigned)(key[j] >> shift) & (kRadix - 1)) : kRadix;  // invalid lanes group apart
+    const unsigned peers = __match_any_sync(PLO_FULL_MASK, d);
+    int pre = 0;
+    if (valid) pre = s_w[warp][d];
+    __syncwarp();
+    if (valid && lane == (__ffs(peers) - 1)) s_w[warp][d] = pre + __popc(peers);
+    __syncwarp();
+    rank[j] = pre + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { int t = s_w[w][threadIdx.x]; s_w[w][threadIdx.x] = run; run += t; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const int i = base + j * 32 + lane;
+    if (i < n) {
+      const unsigned d = (unsigned)(key[j] >> shift) & (kRadix - 1);
+      const int pos = s_g[d] + s_w[warp][d] + rank[j];
+      keys_out[pos] = key[j];
+      vals_out[pos] = val[j];
+    }
+  }
+}
+
+// ---- leaves and levels --------------------------------------------------------------
+
+// one warp per leaf: gather the sorted points/normals, emit the leaf AABB
+__global__ void __launch_bounds__(256) k_gather_leaves(const int* __restrict__ vals, const float4* __restrict__ praw,
+                                                       const float4* __restrict__ nraw, const int* __restrict__ cidx,
+                                                       int n_raw, int n_pad, int n_leaf_pad, float4* __restrict__ pts,
+                                                       float4* __restrict__ nrm, int* __restrict__ pos_of_cidx,
+                                                       float4* __restrict__ lo0, float4* __restrict__ hi0) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int leaf = blockIdx.x * wpb + (threadIdx.x >> 5); leaf < n_leaf_pad; leaf += gridDim.x * wpb) {
+    const int j = leaf * PLO_LEAF + lane;
+    float4 p = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(-1));
+    float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool fin = false;
+    if (j < n_raw) {
+      const int raw = vals[j];
+      const float4 pr = praw[raw];
+      fin = pr.w != 0.f;
+      if (fin) {
+        const int ci = cidx[raw];
+        p = make_float4(pr.x, pr.y, pr.z, __int_as_float(ci));
+        nn = nraw[raw];
+        pos_of_cidx[ci] = j;
+      }
+    }
+    if (j < n_pad) {   // leaves beyond the last real one only get an (empty) box
+      pts[j] = p;
+      nrm[j] = nn;
+    }
+    float l0 = fin ? p.x : CUDART_INF_F, l1 = fin ? p.y : CUDART_INF_F, l2 = fin ? p.z : CUDART_INF_F;
+    float h0 = fin ? p.x : -CUDART_INF_F, h1 = fin ? p.y : -CUDART_INF_F, h2 = fin ? p.z : -CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l0 = fminf(l0, __shfl_xor_sync(PLO_FULL_MASK, l0, o));
+      l1 = fminf(l1, __shfl_xor_sync(PLO_FULL_MASK, l1, o));
+      l2 = fminf(l2, __shfl_xor_sync(PLO_FULL_MASK, l2, o));
+      h0 = fmaxf(h0, __shfl_xor_sync(PLO_FULL_MASK, h0, o));
+      h1 = fmaxf(h1, __shfl_xor_sync(PLO_FULL_MASK, h1, o));
+      h2 = fmaxf(h2, __shfl_xor_sync(PLO_FULL_MASK, h2, o));
+    }
+    if (lane == 0) {
+      lo0[leaf] = make_float4(l0, l1, l2, 0.f);
+      hi0[leaf] = make_float4(h0, h1, h2, 0.f);
+    }
+  }
+}
+
+// one warp per parent node: union of its 32 children
+__global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ lo_c, const float4* __restrict__ hi_c,
+                                                     int n_child_pad, float4* __restrict__ lo_p,
+                                                     float4* __restrict__ hi_p, int n_par_pad) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int par = blockIdx.x * wpb + (threadIdx.x >> 5); par < n_par_pad; par += gridDim.x * wpb) {
+    const int ch = par * PLO_FANOUT + lane;
+    float4 l = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+    float4 h = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
+    if (ch < n_child_pad) { l = lo_c[ch]; h = hi_c[ch]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l.x = fminf(l.x, __shfl_xor_sync(PLO_FULL_MASK, l.x, o));
+      l.y = fminf(l.y, __shfl_xor_sync(PLO_FULL_MASK, l.y, o));
+      l.z = fminf(l.z, __shfl_xor_sync(PLO_FULL_MASK, l.z, o));
+      h.x = fmaxf(h.x, __shfl_xor_sync(PLO_FULL_MASK, h.x, o));
+      h.y = fmaxf(h.y, __shfl_xor_sync(PLO_FULL_MASK, h.y, o));
+      h.z = fmaxf(h.z, __shfl_xor_sync(PLO_FULL_MASK, h.z, o));
+    }
+    if (lane == 0) { lo_p[par] = l; hi_p[par] = h; }
+  }
+}
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+#define LAUNCH_CHECK(c)                          \
+  do {                                           \
+    (c)->launches++;                             \
+    PLO_CUDA((c), cudaGetLastError());           \
+  } while (0)
+
+int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride) {
+  c->have_target = false;
+  c->pca_valid = false;
+  c->projected = false;
+  c->n_raw_t = n;
+  c->n_levels = 0;
+  DevCounts* dc = c->counts.as<DevCounts>();
+  if (n == 0) {
+    PLO_CUDA(c, cudaMemsetAsync(&dc->n_target, 0, sizeof(int), c->stream));
+    c->n_pad_t = 0;
+    c->have_target = true;
+    return PLO_OK;
+  }
+  if (n > (int64_t)1 << 30) return plo_fail(c, PLO_ERR_UNSUPPORTED, "target larger than 2^30 points");
+  // level geometry (host): cnt[l] nodes, padded to a multiple of 32
+  int64_t cnt[PLO_MAX_LEVELS], pad[PLO_MAX_LEVELS];
+  cnt[0] = (n + PLO_LEAF - 1) / PLO_LEAF;
+  pad[0] = round_up(cnt[0], PLO_FANOUT);
+  int L = 1;
+  while (cnt[L - 1] > PLO_FANOUT) {
+    if (L == PLO_MAX_LEVELS) return plo_fail(c, PLO_ERR_UNSUPPORTED, "too many index levels");
+    cnt[L] = pad[L - 1] / PLO_FANOUT;
+    pad[L] = round_up(cnt[L], PLO_FANOUT);
+    ++L;
+  }
+  const int64_t n_pad = cnt[0] * PLO_LEAF;
+  c->n_pad_t = n_pad;
+  const int nb = (int)((n + kTile - 1) / kTile);
+  const int nbs = (int)((n + kSortTile - 1) / kSortTile);
+  PLO_CUDA(c, c->t_praw.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->t_nraw.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->t_cidx.reserve(sizeof(int) * n));
+  PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * (size_t)(nb + 1)));
+  PLO_CUDA(c, c->bbox.reserve(sizeof(unsigned) * 8));
+  for (int a = 0; a < 2; ++a) {
+    PLO_CUDA(c, c->keys[a].reserve(sizeof(unsigned long long) * n));
+    PLO_CUDA(c, c->vals[a].reserve(sizeof(int) * n));
+  }
+  PLO_CUDA(c, c->hist.reserve(sizeof(int) * (size_t)kRadix * nbs));
+  PLO_CUDA(c, c->pts_sorted.reserve(sizeof(float4) * n_pad));
+  PLO_CUDA(c, c->nrm_sorted.reserve(sizeof(float4) * n_pad));
+  PLO_CUDA(c, c->pos_of_cidx.reserve(sizeof(int) * n));
+  for (int l = 0; l < L; ++l) {
+    PLO_CUDA(c, c->lvl_lo[l].reserve(sizeof(float4) * pad[l]));
+    PLO_CUDA(c, c->lvl_hi[l].reserve(sizeof(float4) * pad[l]));
+  }
+  cudaStream_t s = c->stream;
+  if (c->ev[0]) cudaEventRecord(c->ev[0], s);
+  k_init_bbox<<<1, 32, 0, s>>>(c->bbox.as<unsigned>());
+  LAUNCH_CHECK(c);
+  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, c->t_praw.as<float4>(),
+                                    c->t_nraw.as<float4>(), c->blockcnt.as<int>(), c->bbox.as<unsigned>());
+  LAUNCH_CHECK(c);
+  k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_target);
+  LAUNCH_CHECK(c);
+  k_keys<<<nb, 256, 0, s>>>(c->t_praw.as<float4>(), (int)n, c->blockcnt.as<int>(), c->bbox.as<unsigned>(),
+                            c->t_cidx.as<int>(), c->keys[0].as<unsigned long long>(), c->vals[0].as<int>());
+  LAUNCH_CHECK(c);
+  int cur = 0;
+  for (int shift = 0; shift < kKeyBits; shift += kRadixBits) {
+    k_sort_hist<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), (int)n, shift, nbs, c->hist.as<int>());
+    LAUNCH_CHECK(c);
+    k_scan_exclusive<<<1, 1024, 0, s>>>(c->hist.as<int>(), kRadix * nbs, nullptr);
+    LAUNCH_CHECK(c);
+    k_sort_scatter<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), c->vals[cur].as<int>(),
+                                       c->keys[cur ^ 1].as<unsigned long long>(), c->vals[cur ^ 1].as<int>(), (int)n,
+                                       shift, nbs, c->hist.as<int>());
+    LAUNCH_CHECK(c);
+    cur ^= 1;
+  }
+  {
+    const int64_t warps = pad[0];
+    const int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)plo_grid(c, 16));
+    k_gather_leaves<<<blocks, 256, 0, s>>>(c->vals[cur].as<int>(), c->t_praw.as<float4>(), c->t_nraw.as<float4>(),
+                                           c->t_cidx.as<int>(), (int)n, (int)n_pad, (int)pad[0], c->pts_sorted.as<float4>(),
+                                           c->nrm_sorted.as<float4>(), c->pos_of_cidx.as<int>(),
+                                           c->lvl_lo[0].as<float4>(), c->lvl_hi[0].as<float4>());
+    LAUNCH_CHECK(c);
+  }
+  for (int l = 1; l < L; ++l) {
+    const int blocks = (int)std::min<int64_t>((pad[l] + 7) / 8, (int64_t)plo_grid(c, 16));
+    k_build_level<<<blocks, 256, 0, s>>>(c->lvl_lo[l - 1].as<float4>(), c->lvl_hi[l - 1].as<float4>(), (int)pad[l - 1],
+                                         c->lvl_lo[l].as<float4>(), c->lvl_hi[l].as<float4>(), (int)pad[l]);
+    LAUNCH_CHECK(c);
+  }
+  if (c->ev[1]) { cudaEventRecord(c->ev[1], s); c->ev_index_pending = true; }
+  c->n_levels = L;
+  for (int l = 0; l < L; ++l) c->level_nodes[l] = pad[l];
+  c->have_target = true;
+  return PLO_OK;
+}
+
+int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride) {
+  c->have_source = false;
+  c->projected = false;
+  c->m_raw = n;
+  DevCounts* dc = c->counts.as<DevCounts>();
+  if (n == 0) {
+    PLO_CUDA(c, cudaMemsetAsync(&dc->n_source, 0, sizeof(int), c->stream));
+    c->have_source = true;
+    return PLO_OK;
+  }
+  if (n > (int64_t)1 << 30) return plo_fail(c, PLO_ERR_UNSUPPORTED, "source larger than 2^30 points");
+  const int nb = (int)((n + kTile - 1) / kTile);
+  PLO_CUDA(c, c->s_praw.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->s_nraw.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->s_p.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->s_n.reserve(sizeof(float4) * n));
+  PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * (size_t)(nb + 1)));
+  cudaStream_t s = c->stream;
+  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, c->s_praw.as<float4>(),
+                                    c->s_nraw.as<float4>(), c->blockcnt.as<int>(), nullptr);
+  LAUNCH_CHECK(c);
+  k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_source);
+  LAUNCH_CHECK(c);
+  k_compact_source<<<nb, 256, 0, s>>>(c->s_praw.as<float4>(), c->s_nraw.as<float4>(), (int)n, c->blockcnt.as<int>(),
+                                      c->s_p.as<float4>(), c->s_n.as<float4>());
+  LAUNCH_CHECK(c);
+  c->have_source = true;
+  return PLO_OK;
+}

@@ -1,0 +1,571 @@
+// plo_api.cu — implementation of the C ABI declared in include/plo/plo_c_api.h.
+// Host-side plumbing only: context, parameter flattening, staging copies, launch
+// sequencing of the resident loop (src/laser_odometry.cpp:524-647).  No arithmetic of the
+// hot path happens on the host and there is no CPU fallback.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "plo_internal.cuh"
+
+static std::string g_create_error;
+
+cudaError_t DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e == cudaSuccess) cap = want;
+  return e;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+int plo_fail(plo_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+MapView plo_ctx::map_view() const {
+  MapView m;
+  m.pts = pts_sorted.as<float4>();
+  m.nrm = nrm_sorted.as<float4>();
+  m.nrm_pca = nrm_pca.as<double>();
+  for (int l = 0; l < PLO_MAX_LEVELS; ++l) {
+    m.lo[l] = lvl_lo[l].as<float4>();
+    m.hi[l] = lvl_hi[l].as<float4>();
+  }
+  m.n_levels = n_levels;
+  m.n_raw = (int)n_raw_t;
+  return m;
+}
+
+static void flatten_params(plo_ctx* c) {
+  const plo_params& p = c->prm;
+  DevParams& d = c->dprm;
+  d.h2 = p.h * p.h;                 // src/imls_icp.cpp:620
+  d.r2 = p.r * p.r;                 // libnabo: maxRadius2 = maxRadius * maxRadius
+  d.r_normal2 = p.r_normal * p.r_normal;
+  d.angle_thr = p.angle_diff_threshold;
+  // cosine shortcut of the `angle > thr` test; thresholds outside [0,180) never / always fire
+  if (!(p.angle_diff_threshold < 180.0)) d.cos_thr = -2.0;
+  else if (p.angle_diff_threshold < 0.0) d.cos_thr = 2.0;
+  else d.cos_thr = cos(p.angle_diff_threshold * 3.14159265358979323846 / 180.0);
+  d.delta_dist_thr = p.delta_dist_threshold;
+  d.delta_angle_thr = p.delta_angle_threshold;
+  d.ransac_dist_thr = p.ransac_distance_threshold;
+  d.huber_thr2 = p.huber_threshold * p.ransac_distance_threshold;   // src/solver.cpp:339
+  d.k = p.search_number;
+  d.k_normal = p.search_number_normal;
+  d.use_pca_normals = p.is_get_normals ? 0 : 1;
+  d.angle_constraint = p.normal_angle_constraint ? 1 : 0;
+  d.transform_normal = p.transform_normal ? 1 : 0;
+  d.correspond_number = p.correspond_number;
+  d.weight_mode = p.weight_mode;
+  d.iterations = p.iterations;
+}
+
+extern "C" {
+
+int plo_version(void) { return 100; }
+
+void plo_default_params(plo_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->iterations = 30;                      // config.json:134
+  p->h = 1.0;                              // :91
+  p->r = 3.0;                              // :92
+  p->r_normal = 1.0;                       // :103
+  p->is_get_normals = 1;                   // :102
+  p->search_number_normal = 10;            // :104
+  p->search_number = 20;                   // :116
+  p->normal_angle_constraint = 1;          // :111
+  p->angle_diff_threshold = 30.0;          // :112
+  p->transform_normal = 0;                 // :85
+  p->correspond_number = 6;                // :89
+  p->delta_dist_threshold = 0.001;         // :135
+  p->delta_angle_threshold = 0.0001745353; // :136
+  p->weight_mode = PLO_W_UNIT;
+  p->ransac_distance_threshold = 0.8;      // :146
+  p->huber_threshold = 0.648;              // :148
+}
+
+int plo_create(int device, plo_ctx** out) {
+  if (!out) return plo_fail(nullptr, PLO_ERR_INVALID_ARG, "plo_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return plo_fail(nullptr, PLO_ERR_NO_DEVICE,
+                    std::string("plo_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (device < 0 || device >= ndev) return plo_fail(nullptr, PLO_ERR_INVALID_ARG, "plo_create: bad device ordinal");
+  plo_ctx* c = new (std::nothrow) plo_ctx();
+  if (!c) return plo_fail(nullptr, PLO_ERR_STATE, "plo_create: out of host memory");
+  c->device = device;
+  plo_default_params(&c->prm);
+  flatten_params(c);
+#define CREATE_CUDA(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      plo_fail(nullptr, PLO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+      plo_destroy(c);                                                                       \
+      return PLO_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    plo_fail(nullptr, PLO_ERR_UNSUPPORTED, "plo_create: device is not sm_100 class (library is built for sm_100a only)");
+    plo_destroy(c);
+    return PLO_ERR_UNSUPPORTED;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  for (int i = 0; i < 4; ++i) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  CREATE_CUDA(c->state.reserve(sizeof(DevState)));
+  CREATE_CUDA(c->counts.reserve(sizeof(DevCounts)));
+  CREATE_CUDA(cudaMemsetAsync(c->counts.p, 0, sizeof(DevCounts), c->stream));
+  CREATE_CUDA(cudaMemsetAsync(c->state.p, 0, sizeof(DevState), c->stream));
+  CREATE_CUDA(cudaMallocHost(&c->h_state, sizeof(DevState)));
+  CREATE_CUDA(cudaMallocHost(&c->h_counts, sizeof(DevCounts)));
+  CREATE_CUDA(cudaStreamSynchronize(c->stream));
+#undef CREATE_CUDA
+  *out = c;
+  return PLO_OK;
+}
+
+void plo_destroy(plo_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->t_stage, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
+                    &c->vals[0], &c->vals[1], &c->hist, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status,
+                    &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->partials, &c->state,
+                    &c->counts, &c->scratch, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
+  for (DevBuf* b : bufs) b->release();
+  for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* plo_last_error(const plo_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int plo_set_stream(plo_ctx* c, void* cuda_stream) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->own_stream = false;
+  return PLO_OK;
+}
+
+int plo_synchronize(plo_ctx* c) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int plo_set_params(plo_ctx* c, const plo_params* p) {
+  if (!c || !p) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: NULL argument");
+  if (p->search_number < 1 || p->search_number > PLO_MAX_K)
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_set_params: search_number must be in [1, 32]");
+  if (!p->is_get_normals && (p->search_number_normal < 1 || p->search_number_normal > PLO_MAX_K))
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_set_params: search_number_normal must be in [1, 32]");
+  if (p->iterations < 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: iterations < 0");
+  if (!(p->r >= 0.0) || !(p->h >= 0.0) || !(p->r_normal >= 0.0))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: h, r, r_normal must be >= 0");
+  if (p->weight_mode != PLO_W_UNIT && p->weight_mode != PLO_W_HUBER_EXP)
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown weight_mode");
+  const bool pca_changed = c->prm.r_normal != p->r_normal || c->prm.search_number_normal != p->search_number_normal ||
+                           c->prm.is_get_normals != p->is_get_normals;
+  c->prm = *p;
+  flatten_params(c);
+  if (pca_changed) c->pca_valid = false;
+  c->hooks_valid = false;
+  return PLO_OK;
+}
+
+static int stage_and_run(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride, DevBuf& stage, bool target) {
+  if (n < 0 || (n > 0 && !host_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "set cloud: bad pointer / count");
+  if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "set cloud: stride must be >= 28 and a multiple of 4");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  if (n > 0) {
+    PLO_CUDA(c, stage.reserve((size_t)n * stride));
+    PLO_CUDA(c, cudaMemcpyAsync(stage.p, host_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+  }
+  return target ? plo_build_index(c, stage.p, n, stride) : plo_upload_source(c, stage.p, n, stride);
+}
+
+int plo_set_target(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  return stage_and_run(c, host_pts, n, stride, c->t_stage, true);
+}
+
+int plo_set_source(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  return stage_and_run(c, host_pts, n, stride, c->s_stage, false);
+}
+
+int plo_set_target_device(plo_ctx* c, const void* dev_pts, int64_t n, int32_t stride) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !dev_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_target_device: bad pointer / count");
+  if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_target_device: bad stride");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  return plo_build_index(c, dev_pts, n, stride);
+}
+
+int plo_set_source_device(plo_ctx* c, const void* dev_pts, int64_t n, int32_t stride) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !dev_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_source_device: bad pointer / count");
+  if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_source_device: bad stride");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  return plo_upload_source(c, dev_pts, n, stride);
+}
+
+static int fetch_counts(plo_ctx* c) {
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaMemcpyAsync(c->h_counts, c->counts.p, sizeof(DevCounts), cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int64_t plo_target_size(plo_ctx* c) {
+  if (!c || !c->have_target) return -1;
+  if (fetch_counts(c) != PLO_OK) return -1;
+  return c->h_counts->n_target;
+}
+
+int64_t plo_source_size(plo_ctx* c) {
+  if (!c || !c->have_source) return -1;
+  if (fetch_counts(c) != PLO_OK) return -1;
+  return c->h_counts->n_source;
+}
+
+static int require_clouds(plo_ctx* c, const char* who) {
+  if (!c->have_target) return plo_fail(c, PLO_ERR_STATE, std::string(who) + ": no target cloud set");
+  if (!c->have_source) return plo_fail(c, PLO_ERR_STATE, std::string(who) + ": no source cloud set");
+  return PLO_OK;
+}
+
+static int fetch_state(plo_ctx* c) {
+  PLO_CUDA(c, cudaMemcpyAsync(c->h_state, c->state.p, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaMemcpyAsync(c->h_counts, c->counts.p, sizeof(DevCounts), cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int plo_project(plo_ctx* c, const double T[16], int32_t hooks, plo_proj_stats* stats) {
+  if (!c || !T) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_project: NULL argument");
+  PLO_TRY(require_clouds(c, "plo_project"));
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(plo_reserve_query_buffers(c, hooks != 0));
+  if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
+  PLO_TRY(plo_launch_init_state(c, T));
+  PLO_TRY(plo_launch_project(c, hooks != 0));
+  c->projected = true;
+  c->hooks_valid = hooks != 0;
+  if (stats) {
+    // the drop counters come out of the same reduction the solver uses
+    PLO_TRY(plo_launch_reduce_solve(c, false));
+    PLO_TRY(fetch_state(c));
+    stats->n_source = c->h_counts->n_source;
+    stats->n_pairs = c->h_state->pairs;
+    for (int i = 0; i < 6; ++i) stats->dropped[i] = c->h_state->dropped[i];
+  }
+  return PLO_OK;
+}
+
+int plo_get_pairs(plo_ctx* c, float* src_xyz, float* ref_xyz, float* ref_n, int32_t* src_idx, int64_t cap, int64_t* n) {
+  if (!c || !n) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_get_pairs: NULL argument");
+  if (!c->projected) return plo_fail(c, PLO_ERR_STATE, "plo_get_pairs: call plo_project first");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  const size_t m = (size_t)std::max<int64_t>(c->m_raw, 1);
+  PLO_CUDA(c, c->h_src.reserve(sizeof(float) * 3 * m));
+  PLO_CUDA(c, c->h_ref.reserve(sizeof(float) * 3 * m));
+  PLO_CUDA(c, c->h_nrm.reserve(sizeof(float) * 3 * m));
+  PLO_CUDA(c, c->h_w.reserve(sizeof(int32_t) * m));
+  PLO_TRY(plo_launch_compact_pairs(c, c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->h_w.as<int32_t>()));
+  PLO_TRY(fetch_counts(c));
+  const int64_t np = c->h_counts->n_pairs;
+  *n = np;
+  if (np > cap && (src_xyz || ref_xyz || ref_n || src_idx))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_get_pairs: capacity too small");
+  if (np > 0) {
+    if (src_xyz) PLO_CUDA(c, cudaMemcpyAsync(src_xyz, c->h_src.p, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, c->stream));
+    if (ref_xyz) PLO_CUDA(c, cudaMemcpyAsync(ref_xyz, c->h_ref.p, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, c->stream));
+    if (ref_n) PLO_CUDA(c, cudaMemcpyAsync(ref_n, c->h_nrm.p, sizeof(float) * 3 * np, cudaMemcpyDeviceToHost, c->stream));
+    if (src_idx) PLO_CUDA(c, cudaMemcpyAsync(src_idx, c->h_w.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, c->stream));
+    PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return PLO_OK;
+}
+
+int plo_get_neighbors(plo_ctx* c, int32_t* nn_idx, double* nn_d2, int32_t* nn1_idx, double* nn1_d2) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (!c->projected || !c->hooks_valid) return plo_fail(c, PLO_ERR_STATE, "plo_get_neighbors: last plo_project had hooks == 0");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(fetch_counts(c));
+  const size_t m = (size_t)c->h_counts->n_source;
+  const size_t k = (size_t)c->prm.search_number;
+  if (m == 0) return PLO_OK;
+  if (nn_idx) PLO_CUDA(c, cudaMemcpyAsync(nn_idx, c->q_nn_idx.p, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, c->stream));
+  if (nn_d2) PLO_CUDA(c, cudaMemcpyAsync(nn_d2, c->q_nn_d2.p, sizeof(double) * m * k, cudaMemcpyDeviceToHost, c->stream));
+  if (nn1_idx) PLO_CUDA(c, cudaMemcpyAsync(nn1_idx, c->q_nn1_idx.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (nn1_d2) PLO_CUDA(c, cudaMemcpyAsync(nn1_d2, c->q_nn1_d2.p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int plo_get_query_results(plo_ctx* c, int32_t* status, double* height) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (!c->projected) return plo_fail(c, PLO_ERR_STATE, "plo_get_query_results: call plo_project first");
+  if (height && !c->hooks_valid) return plo_fail(c, PLO_ERR_STATE, "plo_get_query_results: heights need hooks != 0");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(fetch_counts(c));
+  const size_t m = (size_t)c->h_counts->n_source;
+  if (m == 0) return PLO_OK;
+  if (status) PLO_CUDA(c, cudaMemcpyAsync(status, c->q_status.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (height) PLO_CUDA(c, cudaMemcpyAsync(height, c->q_height.p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+}  // extern "C"
+
+// gather of the target normals into stripped-cloud order (device helper kernel)
+__global__ void k_export_normals(const float4* __restrict__ nrm, const double* __restrict__ nrm_pca,
+                                 const int* __restrict__ pos_of_cidx, const DevCounts* __restrict__ counts, int use_pca,
+                                 double* __restrict__ out) {
+  const int n = counts->n_target;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int pos = pos_of_cidx[i];
+    if (use_pca) {
+      out[3 * (size_t)i] = nrm_pca[3 * (size_t)pos];
+      out[3 * (size_t)i + 1] = nrm_pca[3 * (size_t)pos + 1];
+      out[3 * (size_t)i + 2] = nrm_pca[3 * (size_t)pos + 2];
+    } else {
+      const float4 v = nrm[pos];
+      out[3 * (size_t)i] = (double)v.x;
+      out[3 * (size_t)i + 1] = (double)v.y;
+      out[3 * (size_t)i + 2] = (double)v.z;
+    }
+  }
+}
+
+extern "C" {
+
+int plo_get_target_normals(plo_ctx* c, double* out) {
+  if (!c || !out) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_get_target_normals: NULL argument");
+  if (!c->have_target) return plo_fail(c, PLO_ERR_STATE, "plo_get_target_normals: no target cloud set");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  if (c->n_raw_t == 0) return PLO_OK;
+  if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
+  PLO_CUDA(c, c->scratch.reserve(sizeof(double) * 3 * (size_t)c->n_raw_t));
+  k_export_normals<<<plo_grid(c, 4), 256, 0, c->stream>>>(c->nrm_sorted.as<float4>(), c->nrm_pca.as<double>(),
+                                                          c->pos_of_cidx.as<int>(), c->counts.as<DevCounts>(),
+                                                          c->dprm.use_pca_normals, c->scratch.as<double>());
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  PLO_TRY(fetch_counts(c));
+  const size_t n = (size_t)c->h_counts->n_target;
+  if (n > 0) {
+    PLO_CUDA(c, cudaMemcpyAsync(out, c->scratch.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return PLO_OK;
+}
+
+int plo_solve_wls(plo_ctx* c, double delta[16], int32_t* rank) {
+  if (!c || !delta) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_wls: NULL argument");
+  if (!c->projected) return plo_fail(c, PLO_ERR_STATE, "plo_solve_wls: call plo_project first");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(plo_launch_reduce_solve(c, false));
+  PLO_TRY(fetch_state(c));
+  memcpy(delta, c->h_state->delta, sizeof(double) * 16);
+  if (rank) *rank = c->h_state->rank;
+  return PLO_OK;
+}
+
+int plo_solve_wls_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, const double* w, int64_t n,
+                       double delta[16], int32_t* rank) {
+  if (!c || !delta || n < 0 || (n > 0 && (!src || !ref || !nrm)))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_wls_host: bad argument");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  const size_t bytes = sizeof(double) * 3 * (size_t)std::max<int64_t>(n, 1);
+  PLO_CUDA(c, c->h_src.reserve(bytes));
+  PLO_CUDA(c, c->h_ref.reserve(bytes));
+  PLO_CUDA(c, c->h_nrm.reserve(bytes));
+  if (w) PLO_CUDA(c, c->h_w.reserve(sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+  if (n > 0) {
+    PLO_CUDA(c, cudaMemcpyAsync(c->h_src.p, src, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    PLO_CUDA(c, cudaMemcpyAsync(c->h_ref.p, ref, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    PLO_CUDA(c, cudaMemcpyAsync(c->h_nrm.p, nrm, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (w) PLO_CUDA(c, cudaMemcpyAsync(c->h_w.p, w, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  PLO_TRY(plo_launch_reduce_solve_host_pairs(c, c->h_src.as<double>(), c->h_ref.as<double>(), c->h_nrm.as<double>(),
+                                             w ? c->h_w.as<double>() : nullptr, n));
+  PLO_TRY(fetch_state(c));
+  memcpy(delta, c->h_state->delta, sizeof(double) * 16);
+  if (rank) *rank = c->h_state->rank;
+  return PLO_OK;
+}
+
+int plo_get_normal_equations(plo_ctx* c, double H21[21], double g6[6], double* sw, double* swbb, int64_t* count) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(fetch_state(c));
+  if (H21) memcpy(H21, c->h_state->H, sizeof(double) * 21);
+  if (g6) memcpy(g6, c->h_state->g, sizeof(double) * 6);
+  if (sw) *sw = c->h_state->sw;
+  if (swbb) *swbb = c->h_state->swbb;
+  if (count) *count = c->h_state->pairs;
+  return PLO_OK;
+}
+
+static int enqueue_register(plo_ctx* c, const double* T0) {
+  PLO_TRY(plo_reserve_query_buffers(c, false));
+  if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
+  PLO_TRY(plo_launch_init_state(c, T0));
+  // every iteration is enqueued up front; kernels of iterations after convergence see the
+  // device-side `done` flag and return at once — no host round trip inside the loop
+  for (int it = 0; it < c->prm.iterations; ++it) {
+    PLO_TRY(plo_launch_project(c, false));
+    PLO_TRY(plo_launch_reduce_solve(c, true));
+  }
+  c->projected = true;
+  c->hooks_valid = false;
+  return PLO_OK;
+}
+
+static void fill_reg_stats(const DevState* s, plo_reg_stats* st, int iterations) {
+  st->status = s->status ? s->status : (iterations == 0 ? PLO_REG_MAX_ITERS : s->status);
+  st->iters = s->iters;
+  st->pairs = s->pairs;
+  st->rms = s->rms;
+  for (int i = 0; i < 6; ++i) st->dropped[i] = s->dropped[i];
+  st->delta_dist = s->delta_dist;
+  st->delta_angle = s->delta_angle;
+  st->rank = s->rank;
+  st->reserved = 0;
+}
+
+int plo_register(plo_ctx* c, const double T0[16], double T[16], plo_reg_stats* stats) {
+  if (!c || !T) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register: NULL argument");
+  PLO_TRY(require_clouds(c, "plo_register"));
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  cudaEventRecord(c->ev[2], c->stream);
+  PLO_TRY(enqueue_register(c, T0));
+  cudaEventRecord(c->ev[3], c->stream);
+  c->ev_reg_pending = true;
+  PLO_TRY(fetch_state(c));
+  memcpy(T, c->h_state->rPose, sizeof(double) * 16);
+  if (stats) fill_reg_stats(c->h_state, stats, c->prm.iterations);
+  return PLO_OK;
+}
+
+// copies the loop state of one finished registration into a device-side result slot
+__global__ void k_store_result(const DevState* __restrict__ st, DevState* __restrict__ slot) {
+  if (threadIdx.x == 0) *slot = *st;
+}
+
+int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, const int64_t* n_src,
+                       const void* const* targets, const int64_t* n_tgt, int32_t stride, int32_t on_device,
+                       double* T_out, plo_reg_stats* stats_out) {
+  if (!c || count < 0 || (count > 0 && (!sources || !n_src || !targets || !n_tgt || !T_out)))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad argument");
+  if (count == 0) return PLO_OK;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  DevBuf slots;
+  PLO_CUDA(c, slots.reserve(sizeof(DevState) * (size_t)count));
+  DevState* h_slots = nullptr;
+  PLO_CUDA(c, cudaMallocHost(&h_slots, sizeof(DevState) * (size_t)count));
+  int rc = PLO_OK;
+  for (int i = 0; i < count && rc == PLO_OK; ++i) {
+    // the staging buffers are reused pair after pair: stream order keeps that safe
+    rc = on_device ? plo_set_target_device(c, targets[i], n_tgt[i], stride) : plo_set_target(c, targets[i], n_tgt[i], stride);
+    if (rc == PLO_OK) rc = on_device ? plo_set_source_device(c, sources[i], n_src[i], stride) : plo_set_source(c, sources[i], n_src[i], stride);
+    if (rc == PLO_OK) rc = enqueue_register(c, nullptr);
+    if (rc == PLO_OK) {
+      k_store_result<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), slots.as<DevState>() + i);
+      c->launches++;
+      if (cudaGetLastError() != cudaSuccess) rc = plo_fail(c, PLO_ERR_CUDA, "plo_register_batch: k_store_result launch failed");
+    }
+  }
+  if (rc == PLO_OK) {
+    cudaError_t e = cudaMemcpyAsync(h_slots, slots.p, sizeof(DevState) * (size_t)count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = plo_fail(c, PLO_ERR_CUDA, std::string("plo_register_batch: ") + cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(c->stream);
+  }
+  if (rc == PLO_OK) {
+    for (int i = 0; i < count; ++i) {
+      memcpy(T_out + 16 * (size_t)i, h_slots[i].rPose, sizeof(double) * 16);
+      if (stats_out) fill_reg_stats(&h_slots[i], &stats_out[i], c->prm.iterations);
+    }
+  }
+  cudaFreeHost(h_slots);
+  slots.release();
+  return rc;
+}
+
+int64_t plo_launch_count(const plo_ctx* c) { return c ? c->launches : 0; }
+
+int plo_last_timings(plo_ctx* c, float* ms_index_build, float* ms_register) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->ev_index_pending) { cudaEventElapsedTime(&c->ms_index, c->ev[0], c->ev[1]); c->ev_index_pending = false; }
+  if (c->ev_reg_pending) { cudaEventElapsedTime(&c->ms_register, c->ev[2], c->ev[3]); c->ev_reg_pending = false; }
+  if (ms_index_build) *ms_index_build = c->ms_index;
+  if (ms_register) *ms_register = c->ms_register;
+  return PLO_OK;
+}
+
+int plo_time_project_kernel(plo_ctx* c, const double T[16], int32_t reps, float* ms_mean) {
+  if (!c || !T || !ms_mean || reps < 1) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_time_project_kernel: bad argument");
+  PLO_TRY(require_clouds(c, "plo_time_project_kernel"));
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(plo_reserve_query_buffers(c, false));
+  if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
+  PLO_TRY(plo_launch_init_state(c, T));
+  PLO_TRY(plo_launch_project(c, false));   // warm-up
+  cudaEvent_t a, b;
+  PLO_CUDA(c, cudaEventCreate(&a));
+  PLO_CUDA(c, cudaEventCreate(&b));
+  cudaEventRecord(a, c->stream);
+  for (int i = 0; i < reps; ++i) PLO_TRY(plo_launch_project(c, false));
+  cudaEventRecord(b, c->stream);
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *ms_mean = ms / reps;
+  c->projected = true;
+  c->hooks_valid = false;
+  return PLO_OK;
+}
+
+}  // extern "C"

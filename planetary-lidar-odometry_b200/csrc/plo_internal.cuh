@@ -1,0 +1,159 @@
+// plo_internal.cuh — shared declarations of the CUDA implementation behind plo_c_api.h.
+// Compiled for sm_100a only.  The whole library is built with -fmad=false: the distance,
+// box-bound and transform arithmetic must round exactly like the reference's double code
+// (no FMA contraction) so that neighbour sets are bit-exact.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "plo/plo_c_api.h"
+
+#define PLO_MAX_LEVELS 6          // 32 points/leaf * 32^5 nodes > 1e9 points
+#define PLO_LEAF 32               // points per leaf == warp size
+#define PLO_FANOUT 32             // children per internal node == warp size
+#define PLO_MAX_K 32              // neighbour list lives one entry per lane
+#define PLO_NSUM 36               // 21 H + 6 g + sw + swbb + count + 6 drop counters
+#define PLO_FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------------
+// device-side views
+// ---------------------------------------------------------------------------------
+
+// Spatial index over the target ("map"): points sorted by 48-bit Morton key, cut into
+// leaves of 32 consecutive points; level l+1 groups 32 consecutive nodes of level l.
+// Every level stores one AABB per node as two float4 (lo.xyz, hi.xyz); arrays are padded
+// to a multiple of 32 nodes with empty boxes (lo=+inf, hi=-inf).
+struct MapView {
+  const float4* pts;      // [n_pad] sorted: x,y,z, w = int bits of the stripped-cloud index
+  const float4* nrm;      // [n_pad] sorted: delivered normals (float), w unused
+  const double* nrm_pca;  // [3*n_pad] sorted: PCA normals (double) when !is_get_normals
+  const float4* lo[PLO_MAX_LEVELS];
+  const float4* hi[PLO_MAX_LEVELS];
+  int n_levels;           // stored levels; level n_levels-1 has <= 32 nodes
+  int n_raw;              // points uploaded (before strip); 0 => empty map
+};
+
+// Device-resident loop state: written by the solve kernel, read by the next projection.
+struct DevState {
+  double rPose[16];
+  double delta[16];
+  double H[21];
+  double g[6];
+  double sw, swbb;
+  double rms, delta_dist, delta_angle;
+  long long pairs;
+  long long dropped[6];
+  int iters;      // solves performed
+  int status;     // 0 while running, else plo_reg_status
+  int rank;
+  int done;       // kernels of later iterations return immediately when set
+};
+
+struct DevCounts {
+  int n_target;   // finite target points
+  int n_source;   // finite source points
+  int n_pairs;    // compaction result of plo_get_pairs
+  int pad;
+};
+
+// kernel-side copy of the parameters that matter on the device
+struct DevParams {
+  double h2, r2, r_normal2;
+  double angle_thr, cos_thr;
+  double delta_dist_thr, delta_angle_thr;
+  double ransac_dist_thr, huber_thr2;
+  int k, k_normal;
+  int use_pca_normals, angle_constraint, transform_normal;
+  int correspond_number, weight_mode, iterations;
+};
+
+// ---------------------------------------------------------------------------------
+// host-side context
+// ---------------------------------------------------------------------------------
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes);
+  void release();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct plo_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  plo_params prm;
+  DevParams dprm;
+  std::string err;
+  int64_t launches = 0;
+
+  // target
+  int64_t n_raw_t = 0;
+  int64_t n_pad_t = 0;
+  bool have_target = false;
+  bool pca_valid = false;
+  int n_levels = 0;
+  int64_t level_nodes[PLO_MAX_LEVELS] = {0};
+  DevBuf t_stage, t_praw, t_nraw, t_cidx, blockcnt, bbox;
+  DevBuf keys[2], vals[2], hist;
+  DevBuf pts_sorted, nrm_sorted, nrm_pca, pos_of_cidx;
+  DevBuf lvl_lo[PLO_MAX_LEVELS], lvl_hi[PLO_MAX_LEVELS];
+
+  // source
+  int64_t m_raw = 0;
+  bool have_source = false;
+  DevBuf s_stage, s_praw, s_nraw, s_p, s_n;
+
+  // per-query results of the last projection
+  DevBuf q_x, q_y, q_n, q_status;
+  bool hooks_valid = false;
+  DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2;
+  bool projected = false;
+
+  // reduction / solve
+  DevBuf partials, state, counts, scratch;
+  DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
+  DevState* h_state = nullptr;       // pinned
+  DevCounts* h_counts = nullptr;     // pinned
+
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms_index = 0.f, ms_register = 0.f;
+  bool ev_index_pending = false, ev_reg_pending = false;
+
+  MapView map_view() const;
+};
+
+int plo_fail(plo_ctx* c, int code, const std::string& msg);
+#define PLO_CUDA(c, expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return plo_fail((c), PLO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+#define PLO_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != PLO_OK) return _r; \
+  } while (0)
+
+// launch geometry: persistent grids sized from the SM count
+static inline int plo_grid(const plo_ctx* c, int blocks_per_sm) { return c->sm_count * blocks_per_sm; }
+
+// ---- index_build.cu ---------------------------------------------------------------
+int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
+int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
+// ---- knn_project.cu ---------------------------------------------------------------
+int plo_launch_pca_normals(plo_ctx* c);
+int plo_launch_project(plo_ctx* c, bool hooks);
+int plo_reserve_query_buffers(plo_ctx* c, bool hooks);
+// ---- p2plane_solve.cu -------------------------------------------------------------
+int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop);
+int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const double* d_ref,
+                                       const double* d_nrm, const double* d_w, int64_t n);
+int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null);
+int plo_launch_compact_pairs(plo_ctx* c, float* d_src, float* d_ref, float* d_nrm, int32_t* d_idx);

@@ -1,0 +1,101 @@
+"""CPU-only checks of the boundary and the host logic (no compute calls):
+the C-ABI library loads, exports every symbol include/plo/plo_c_api.h declares, fails loudly
+without a GPU; config.json flattening mirrors the reference's dispatch and rejects what is out
+of scope."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import plo_b200 as plo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "plo", "plo_c_api.h")).read()
+    return sorted(set(re.findall(r"PLO_API\s+[\w\s\*]+?\b(plo_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 25
+    L = plo._lib.lib()
+    for n in names:
+        assert hasattr(L, n), f"libplo_cuda.so does not export {n}"
+    assert sorted(plo._lib.EXPORTS) == names
+    assert L.plo_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives the ABI structs (checked against ctypes mirrors)
+    src = '#include "plo/plo_c_api.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n", sizeof(plo_params), sizeof(plo_proj_stats), sizeof(plo_reg_stats));return 0;}'
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    assert [int(x) for x in out] == [C.sizeof(plo._lib.PloParams), C.sizeof(plo._lib.PloProjStats), C.sizeof(plo._lib.PloRegStats)]
+
+
+def test_defaults_match_reference_config_json():
+    p = plo.default_params()
+    assert (p.iterations, p.h, p.r, p.r_normal) == (30, 1.0, 3.0, 1.0)
+    assert (p.is_get_normals, p.search_number_normal, p.search_number) == (1, 10, 20)
+    assert (p.normal_angle_constraint, p.angle_diff_threshold, p.transform_normal, p.correspond_number) == (1, 30.0, 0, 6)
+    assert (p.delta_dist_threshold, p.delta_angle_threshold) == (0.001, 0.0001745353)
+    assert (p.ransac_distance_threshold, p.huber_threshold) == (0.8, 0.648)
+
+
+def test_no_gpu_fails_loudly():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(plo.PloError) as e:
+        plo.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_config_flattening_and_rejections(tmp_path):
+    cfg = plo.config.load_config()
+    p = plo.config.params_from_config(cfg)
+    assert p.search_number == 20 and p.weight_mode == 0
+    # the reference's own config.json layout (only the keys the path reads)
+    ref_like = json.loads(json.dumps(cfg))
+    ref_like["laser_odometry"]["solve_method"]["method"] = "RANSAC"
+    ref_like["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "Weighted LS"
+    f = tmp_path / "config.json"
+    f.write_text(json.dumps(ref_like))
+    p = plo.config.params_from_config(plo.config.load_config(str(f)))
+    assert p.weight_mode == 1
+    for mutate, msg in [
+        (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "plane_ICP"), "plane_ICP"),
+        (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "bogus"), "Invalid MATCHING_METHOD"),
+        (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "Teaser"), "Teaser"),
+        (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "nope"), "Invalid SOLVE_METHOD"),
+        (lambda c: c["laser_odometry"]["solve_method"]["RANSAC"].__setitem__("final_solve_method", "DRPM"), "DRPM"),
+        (lambda c: c["laser_odometry"]["matching_method"]["IMLS"]["use_tensor_voting"].__setitem__("enabled", True), "tensor"),
+        (lambda c: c.__setitem__("backend", "cpu"), "no CPU fallback"),
+    ]:
+        c2 = json.loads(json.dumps(ref_like))
+        mutate(c2)
+        with pytest.raises(plo.config.ConfigError) as e:
+            plo.config.params_from_config(c2)
+        assert msg in str(e.value)
+
+
+def test_tum_pose_format(tmp_path):
+    T = plo.synth.scenes.pose_matrix([1.5, -2.25, 0.125], yaw_deg=90)
+    f = tmp_path / "poses.txt"
+    plo.save_poses_tum(str(f), [np.eye(4), T])
+    lines = f.read_text().strip().split("\n")
+    assert lines[0] == "0.000000 0.000000 0.000000 0.000000 0.000000 0.000000 0.000000 1.000000"
+    v = [float(x) for x in lines[1].split()]
+    assert v[1:4] == [1.5, -2.25, 0.125] and abs(v[6] - np.sqrt(0.5)) < 1e-6 and abs(v[7] - np.sqrt(0.5)) < 1e-6
