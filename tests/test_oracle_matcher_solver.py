@@ -37,8 +37,8 @@ def _compare_projection(oracle_mod, target, source, T=None, **kw):
     assert np.array_equal(a["src_idx"], b["src_idx"])
     ok = a["status"] == 0
     if ok.any():
-        rel = np.abs(a["height"][ok] - b["height"][ok]) / np.maximum(np.abs(b["height"][ok]), 1e-12)
-        assert rel.max() <= 1e-9
+        err = np.abs(a["height"][ok] - b["height"][ok])
+        assert (err <= 1e-9 * np.abs(b["height"][ok]) + 1e-12).all()
         assert np.array_equal(a["src_xyz"], b["src_xyz"])
         assert np.abs(a["ref_xyz"].astype(np.float64) - b["ref_xyz"]).max() <= 1e-6
         assert np.array_equal(a["ref_n"], b["ref_n"])
