@@ -161,6 +161,9 @@ PLO_API int plo_get_pairs(plo_ctx* ctx, float* src_xyz, float* ref_xyz, float* r
  * nn1_idx[M] / nn1_d2[M]: the 1-NN of :601-609.  Any pointer may be NULL. */
 PLO_API int plo_get_neighbors(plo_ctx* ctx, int32_t* nn_idx, double* nn_d2,
                               int32_t* nn1_idx, double* nn1_d2);
+/* traversal statistics of the k-NN search per query (hooks != 0): stats3[3*M] =
+ * leaves scanned, internal nodes expanded, list insertions — for the roofline analysis */
+PLO_API int plo_get_search_stats(plo_ctx* ctx, int32_t* stats3);
 /* status[M] (plo_point_status), height[M] = I(x) of :480 (NaN where not computed) */
 PLO_API int plo_get_query_results(plo_ctx* ctx, int32_t* status, double* height);
 /* normals the matcher uses for the target, n x 3 doubles in stripped-cloud order:
@@ -209,6 +212,12 @@ PLO_API int64_t plo_launch_count(const plo_ctx* ctx);
 /* device milliseconds of the last index build / last registration loop, measured with
  * CUDA events on the context's stream (0 if not measured yet) */
 PLO_API int plo_last_timings(plo_ctx* ctx, float* ms_index_build, float* ms_register);
+/* per-kernel CUDA-event timing inside plo_register (off by default): when enabled every
+ * projection-kernel launch of the resident loop is bracketed by an event pair on the
+ * context's stream.  plo_last_kernel_timings returns the mean device ms of the launches
+ * that did work in the last plo_register and how many those were. */
+PLO_API int plo_set_profiling(plo_ctx* ctx, int32_t enabled);
+PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_t* n_project);
 /* per-kernel timing of one projection pass for the roofline: runs the projection kernel
  * `reps` times at the current pose and returns the mean device ms per launch */
 PLO_API int plo_time_project_kernel(plo_ctx* ctx, const double T[16], int32_t reps, float* ms_mean);

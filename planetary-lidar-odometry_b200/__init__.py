@@ -8,7 +8,7 @@ matcher/solver/driver interface over ctypes.  There is no CPU fallback: using th
 classes without the built library, or without a GPU, fails loudly.
 """
 from . import synth  # noqa: F401
-from . import _lib, config  # noqa: F401
+from . import _lib, config, distributed  # noqa: F401
 from ._lib import PloError, PloParams, default_params  # noqa: F401
 from .context import Context  # noqa: F401
 from .matcher import IMLSICPMatcher  # noqa: F401

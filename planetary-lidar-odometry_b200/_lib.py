@@ -51,9 +51,10 @@ EXPORTS = [
     "plo_create", "plo_destroy", "plo_last_error", "plo_version", "plo_set_stream", "plo_synchronize",
     "plo_default_params", "plo_set_params", "plo_set_target", "plo_set_source", "plo_set_target_device",
     "plo_set_source_device", "plo_target_size", "plo_source_size", "plo_project", "plo_get_pairs",
-    "plo_get_neighbors", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls",
+    "plo_get_neighbors", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls",
     "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
-    "plo_launch_count", "plo_last_timings", "plo_time_project_kernel",
+    "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
+    "plo_last_kernel_timings",
 ]
 
 
@@ -95,6 +96,7 @@ def lib() -> C.CDLL:
     L.plo_get_pairs.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.plo_get_neighbors.argtypes = [vp, vp, vp, vp, vp]
     L.plo_get_query_results.argtypes = [vp, vp, vp]
+    L.plo_get_search_stats.argtypes = [vp, vp]
     L.plo_get_target_normals.argtypes = [vp, vp]
     L.plo_solve_wls.argtypes = [vp, vp, C.POINTER(i32)]
     L.plo_solve_wls_host.argtypes = [vp, vp, vp, vp, vp, i64, vp, C.POINTER(i32)]
@@ -105,6 +107,8 @@ def lib() -> C.CDLL:
     L.plo_launch_count.restype = i64
     L.plo_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.plo_time_project_kernel.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
+    L.plo_set_profiling.argtypes = [vp, i32]
+    L.plo_last_kernel_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     _lib = L
     return L
 

@@ -138,6 +138,12 @@ class Context:
         self._ck(self.L.plo_get_neighbors(self.h, _ptr(ni), _ptr(nd), _ptr(i1), _ptr(d1)))
         return dict(nn_idx=ni, nn_d2=nd, nn1_idx=i1, nn1_d2=d1)
 
+    def search_stats(self) -> np.ndarray:
+        """(M, 3) int32: leaves scanned, internal nodes expanded, list insertions per query"""
+        out = np.empty((self.n_source, 3), np.int32)
+        self._ck(self.L.plo_get_search_stats(self.h, _ptr(out)))
+        return out
+
     def query_results(self, heights: bool = True):
         m = self.n_source
         st = np.empty(m, np.int32)
@@ -210,6 +216,14 @@ class Context:
         a, b = C.c_float(), C.c_float()
         self._ck(self.L.plo_last_timings(self.h, C.byref(a), C.byref(b)))
         return dict(ms_index_build=a.value, ms_register=b.value)
+
+    def set_profiling(self, enabled: bool):
+        self._ck(self.L.plo_set_profiling(self.h, 1 if enabled else 0))
+
+    def last_kernel_timings(self):
+        ms, n = C.c_float(), C.c_int32()
+        self._ck(self.L.plo_last_kernel_timings(self.h, C.byref(ms), C.byref(n)))
+        return dict(ms_project_mean=ms.value, n_project=n.value)
 
     def time_project_kernel(self, T=None, reps: int = 10) -> float:
         T = np.ascontiguousarray(np.eye(4) if T is None else T, dtype=np.float64).reshape(16)

@@ -47,6 +47,7 @@ struct Search {
   int k;
   unsigned kmask;
   bool allow_self;
+  int n_leaf, n_node, n_ins;   // traversal statistics (reported through the hooks)
 };
 
 __device__ __forceinline__ double dist2(const Query& q, float px, float py, float pz) {
@@ -67,6 +68,7 @@ __device__ __forceinline__ bool better(double d2, int idx, double kd2, int kidx)
 
 __device__ __forceinline__ void visit_leaf(const MapView& m, int leaf, const Query& q, Search& s, TopK& tk, int lane) {
   const float4 p = __ldg(&m.pts[leaf * PLO_LEAF + lane]);
+  s.n_leaf++;
   const double d2 = dist2(q, p.x, p.y, p.z);
   const int cidx = __float_as_int(p.w);
   const bool pass = (d2 <= s.r2) && (s.allow_self || d2 > DBL_EPSILON) && better(d2, cidx, s.kd2, s.kidx);
@@ -77,6 +79,7 @@ __device__ __forceinline__ void visit_leaf(const MapView& m, int leaf, const Que
     const double cd2 = __shfl_sync(PLO_FULL_MASK, d2, src);
     const int ci = __shfl_sync(PLO_FULL_MASK, cidx, src);
     if (!better(cd2, ci, s.kd2, s.kidx)) continue;   // warp-uniform
+    s.n_ins++;
     const bool less = (tk.d2 < cd2) || (tk.d2 == cd2 && tk.idx < ci);
     const int at = __popc(__ballot_sync(PLO_FULL_MASK, less) & s.kmask);
     const double ud2 = __shfl_up_sync(PLO_FULL_MASK, tk.d2, 1);
@@ -94,6 +97,7 @@ struct Visit {
   // `node` is a node of level LEVEL (or the virtual root); its children live in level LEVEL-1
   static __device__ __forceinline__ void run(const MapView& m, int node, const Query& q, Search& s, TopK& tk, int lane) {
     const int child = node * PLO_FANOUT + lane;
+    s.n_node++;
     const double bd = box_dist2(q, __ldg(&m.lo[LEVEL - 1][child]), __ldg(&m.hi[LEVEL - 1][child]));
     // positive floats order like their bit patterns; rounding down keeps the order weakly
     const unsigned key = __float_as_uint(__double2float_rd(bd));
@@ -119,6 +123,7 @@ __device__ __forceinline__ void knn_search(const MapView& m, const Query& q, Sea
   tk.pos = -1;
   s.kd2 = CUDART_INF;
   s.kidx = 0x7fffffff;
+  s.n_leaf = s.n_node = s.n_ins = 0;
   if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) return;
   switch (m.n_levels) {   // warp-uniform
     case 1: Visit<1>::run(m, 0, q, s, tk, lane); break;
@@ -164,6 +169,7 @@ struct ProjectOut {
   double* nn1_d2;
   int* nn_idx;
   double* nn_d2;
+  int* search_stats;   // [M*3] leaves, internal nodes, insertions of the k-NN search
 };
 
 template <bool PCA>
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
     s.allow_self = true;   // :372-375 ALLOW_SELF_MATCH
     TopK tk;
     if (n_tgt > 0) knn_search(m, q, s, tk, lane);
-    else { tk.d2 = CUDART_INF; tk.idx = 0x7fffffff; tk.pos = -1; }
+    else { tk.d2 = CUDART_INF; tk.idx = 0x7fffffff; tk.pos = -1; s.n_leaf = s.n_node = s.n_ins = 0; }
     const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
 
     // ---- 1-NN without self match (:601-609) ----
@@ -293,6 +299,9 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
         out.height[qi] = height;
         out.nn1_idx[qi] = i1;
         out.nn1_d2[qi] = d1;
+        out.search_stats[3 * (size_t)qi] = s.n_leaf;
+        out.search_stats[3 * (size_t)qi + 1] = s.n_node;
+        out.search_stats[3 * (size_t)qi + 2] = s.n_ins;
       }
     }
   }
@@ -384,6 +393,7 @@ int plo_reserve_query_buffers(plo_ctx* c, bool hooks) {
     PLO_CUDA(c, c->q_nn1_d2.reserve(sizeof(double) * m));
     PLO_CUDA(c, c->q_nn_idx.reserve(sizeof(int) * m * c->prm.search_number));
     PLO_CUDA(c, c->q_nn_d2.reserve(sizeof(double) * m * c->prm.search_number));
+    PLO_CUDA(c, c->q_stats.reserve(sizeof(int) * 3 * m));
   }
   return PLO_OK;
 }
@@ -405,6 +415,7 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   out.status = c->q_status.as<int>();
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
+  out.search_stats = c->q_stats.as<int>();
   const int64_t warps = c->m_raw;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)plo_grid(c, 8)));
   if (c->dprm.use_pca_normals)

@@ -156,13 +156,14 @@ void plo_destroy(plo_ctx* c) {
   DevBuf* bufs[] = {&c->t_stage, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
                     &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status,
-                    &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->partials, &c->state,
+                    &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->ev_proj) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -337,6 +338,18 @@ int plo_get_neighbors(plo_ctx* c, int32_t* nn_idx, double* nn_d2, int32_t* nn1_i
   return PLO_OK;
 }
 
+int plo_get_search_stats(plo_ctx* c, int32_t* stats3) {
+  if (!c || !stats3) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_get_search_stats: NULL argument");
+  if (!c->projected || !c->hooks_valid) return plo_fail(c, PLO_ERR_STATE, "plo_get_search_stats: last plo_project had hooks == 0");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_TRY(fetch_counts(c));
+  const size_t m = (size_t)c->h_counts->n_source;
+  if (m == 0) return PLO_OK;
+  PLO_CUDA(c, cudaMemcpyAsync(stats3, c->q_stats.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
 int plo_get_query_results(plo_ctx* c, int32_t* status, double* height) {
   if (!c) return PLO_ERR_INVALID_ARG;
   if (!c->projected) return plo_fail(c, PLO_ERR_STATE, "plo_get_query_results: call plo_project first");
@@ -449,8 +462,17 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
   PLO_TRY(plo_launch_init_state(c, T0));
   // every iteration is enqueued up front; kernels of iterations after convergence see the
   // device-side `done` flag and return at once — no host round trip inside the loop
+  if (c->profiling) {
+    while ((int)c->ev_proj.size() < 2 * c->prm.iterations) {
+      cudaEvent_t e;
+      PLO_CUDA(c, cudaEventCreate(&e));
+      c->ev_proj.push_back(e);
+    }
+  }
   for (int it = 0; it < c->prm.iterations; ++it) {
+    if (c->profiling) cudaEventRecord(c->ev_proj[2 * it], c->stream);
     PLO_TRY(plo_launch_project(c, false));
+    if (c->profiling) cudaEventRecord(c->ev_proj[2 * it + 1], c->stream);
     PLO_TRY(plo_launch_reduce_solve(c, true));
   }
   c->projected = true;
@@ -481,6 +503,32 @@ int plo_register(plo_ctx* c, const double T0[16], double T[16], plo_reg_stats* s
   PLO_TRY(fetch_state(c));
   memcpy(T, c->h_state->rPose, sizeof(double) * 16);
   if (stats) fill_reg_stats(c->h_state, stats, c->prm.iterations);
+  if (c->profiling) {
+    // launches that did work: one per solve, plus the one that found too few pairs
+    int n = c->h_state->iters + (c->h_state->status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0);
+    n = std::min(n, c->prm.iterations);
+    float total = 0.f;
+    for (int it = 0; it < n; ++it) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev_proj[2 * it], c->ev_proj[2 * it + 1]);
+      total += ms;
+    }
+    c->n_project = n;
+    c->ms_project_mean = n > 0 ? total / n : 0.f;
+  }
+  return PLO_OK;
+}
+
+int plo_set_profiling(plo_ctx* c, int32_t enabled) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  c->profiling = enabled != 0;
+  return PLO_OK;
+}
+
+int plo_last_kernel_timings(plo_ctx* c, float* ms_project_mean, int32_t* n_project) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (ms_project_mean) *ms_project_mean = c->ms_project_mean;
+  if (n_project) *n_project = c->n_project;
   return PLO_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "plo/plo_c_api.h"
 
@@ -112,7 +113,7 @@ struct plo_ctx {
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status;
   bool hooks_valid = false;
-  DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2;
+  DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2, q_stats;
   bool projected = false;
 
   // reduction / solve
@@ -124,6 +125,10 @@ struct plo_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_index = 0.f, ms_register = 0.f;
   bool ev_index_pending = false, ev_reg_pending = false;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_proj;   // 2 per loop iteration when profiling
+  float ms_project_mean = 0.f;
+  int n_project = 0;
 
   MapView map_view() const;
 };
