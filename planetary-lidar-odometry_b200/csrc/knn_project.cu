@@ -3,18 +3,28 @@
 // (src/imls_icp.cpp:496-745) with ImplicitMLSFunction (:301-483) fused in, and the
 // per-map-point PCA normal pass (ComputeNormal, :753-794, call sites :411-433,:647-669).
 //
-// One warp per query.  The warp walks the Morton-sorted wide BVH of index_build.cu with
-// warp-uniform control flow: at every internal node the 32 lanes test the 32 child boxes
-// (one coalesced float4 pair per lane), children are visited nearest-first
-// (REDUX min over the box distances); a leaf is one coalesced 512-byte load of 32
-// points, one exact fp64 distance per lane.  The k best neighbours live one per lane
-// in registers, ordered by (d2, index); insertion is a ballot/popc rank plus one
-// shuffle-up.  libnabo's knn semantics are reproduced exactly:
-//   accept iff d2 <= r*r and (allow_self || d2 > DBL_EPSILON), k best ascending,
-//   d2 = ((dx*dx + dy*dy) + dz*dz) in double without FMA, ties by index (D3).
-// A node is pruned iff boxd2 > min(r2, current k-th d2); boxd2 is computed with the same
-// operation order as d2, so by monotonicity of IEEE rounding it never exceeds the d2 of a
-// point inside the box and the strict comparison keeps the result exact even for ties.
+// One warp per query, warp-uniform control flow over the curve-sorted wide BVH of
+// index_build.cu (32 children per node, 32 points per leaf: every node test is one
+// coalesced float4 pair per lane, every leaf one coalesced 512-byte load).  Exact k-NN in
+// three phases:
+//   A  bound: an upper bound D of the k-th neighbour distance (squared).  Triangle inequality
+//      on a reference whose k-th distance is known — the same query in the previous ICP
+//      iteration (temporal) or the previous query of the warp's chunk (carry; LiDAR clouds
+//      arrive in scan order) — D = (sqrt(kd2_ref) + |x - x_ref|)^2, inflated by 1e-9.  Without
+//      a useful reference: greedy descent to the nearest leaves and the k-th smallest
+//      rounded-up distance among their points (bitonic sort / merge across the warp).
+//   B  collect (fp32, conservative): depth-first walk; boxes and points are tested with
+//      float arithmetic in directed rounding (lower bounds of the true distances) against D
+//      rounded up, so the buffered set is a SUPERSET of {p : d2(p) <= D}.  Candidates are
+//      appended to a per-warp shared-memory buffer at ballot/popc offsets — no serial
+//      dependency between candidates.  If the buffer fills, the bound shrinks to the k-th
+//      smallest rounded-up distance buffered so far and the buffer is compacted.
+//   C  select (fp64, exact): d2 = ((dx*dx + dy*dy) + dz*dz) in double without FMA for the
+//      buffered candidates only; libnabo's acceptance rule (d2 <= r*r, self-match epsilon);
+//      each candidate computes its rank under the (d2, index) order (D3: ties by index);
+//      ranks < k are scattered to their slot: lane j then holds the j-th neighbour.
+// Exactness: a point is only ever skipped when a LOWER bound of its distance exceeds an
+// UPPER bound of the k-th distance; the final order is decided on the exact fp64 values.
 //
 // The 1-NN of :601-609 (no self match) is the first list entry with d2 > DBL_EPSILON;
 // only if the list is full of coincident points is a second (k=1) search needed.
@@ -25,13 +35,19 @@
 #include <float.h>
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "plo_internal.cuh"
 
 namespace {
 
-struct Query {
-  double x, y, z;
-};
+constexpr int kCap = 128;          // candidate buffer entries per warp
+constexpr int kWarpsPerBlock = 8;
+constexpr int kGreedyLeaves = 4;   // leaves examined by the greedy phase-A bound
+#ifndef PLO_MINB
+#define PLO_MINB 4
+#endif
 
 // neighbour list: lane j (< k) holds the j-th best entry
 struct TopK {
@@ -40,100 +56,335 @@ struct TopK {
   int pos;   // position in the sorted arrays (for gathers)
 };
 
-struct Search {
-  double r2;
-  double kd2;     // (d2, idx) of the current k-th entry, (+inf, INT_MAX) while not full
-  int kidx;
-  int k;
-  unsigned kmask;
-  bool allow_self;
-  int n_leaf, n_node, n_ins;   // traversal statistics (reported through the hooks)
+struct SearchStats {
+  int n_leaf, n_node, n_cand;
 };
 
-__device__ __forceinline__ double dist2(const Query& q, float px, float py, float pz) {
-  const double dx = __dsub_rn(q.x, (double)px), dy = __dsub_rn(q.y, (double)py), dz = __dsub_rn(q.z, (double)pz);
+struct WarpScratch {
+  double d2[kCap];   // phase C: exact distances
+  int idx[kCap];     // phase C: stripped-cloud indices
+  int pos[kCap];     // phase B: positions of the buffered candidates
+  float lo[kCap];    // phase B: lower bounds of their squared distances
+  double od2[PLO_MAX_K];
+  int oidx[PLO_MAX_K];
+  int opos[PLO_MAX_K];
+};
+
+// ---- conservative fp32 geometry (directed rounding) ------------------------------------
+
+__device__ __forceinline__ float box_lo2(float qx, float qy, float qz, const float4 lo, const float4 hi) {
+  const float ex = fmaxf(fmaxf(__fsub_rd(lo.x, qx), __fsub_rd(qx, hi.x)), 0.f);
+  const float ey = fmaxf(fmaxf(__fsub_rd(lo.y, qy), __fsub_rd(qy, hi.y)), 0.f);
+  const float ez = fmaxf(fmaxf(__fsub_rd(lo.z, qz), __fsub_rd(qz, hi.z)), 0.f);
+  return __fadd_rd(__fadd_rd(__fmul_rd(ex, ex), __fmul_rd(ey, ey)), __fmul_rd(ez, ez));
+}
+
+__device__ __forceinline__ float dist_lo2(float qx, float qy, float qz, const float4 p) {
+  const float ax = fabsf(__fsub_rz(qx, p.x)), ay = fabsf(__fsub_rz(qy, p.y)), az = fabsf(__fsub_rz(qz, p.z));
+  return __fadd_rd(__fadd_rd(__fmul_rd(ax, ax), __fmul_rd(ay, ay)), __fmul_rd(az, az));
+}
+
+// upper bound of the true squared distance from its lower bound (rel. gap of the rd chain < 1e-6)
+__device__ __forceinline__ float hi_from_lo(float lo) { return __fmul_ru(lo, 1.000001f); }
+
+// D (double) -> float threshold for lower-bound tests, with a safety margin
+__device__ __forceinline__ float bound_f(double D) { return __fmul_ru(__double2float_ru(D), 1.000001f); }
+
+__device__ __forceinline__ double dist2_exact(double qx, double qy, double qz, const float4 p) {
+  const double dx = __dsub_rn(qx, (double)p.x), dy = __dsub_rn(qy, (double)p.y), dz = __dsub_rn(qz, (double)p.z);
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ double box_dist2(const Query& q, const float4 lo, const float4 hi) {
-  const double ex = fmax(fmax(__dsub_rn((double)lo.x, q.x), __dsub_rn(q.x, (double)hi.x)), 0.0);
-  const double ey = fmax(fmax(__dsub_rn((double)lo.y, q.y), __dsub_rn(q.y, (double)hi.y)), 0.0);
-  const double ez = fmax(fmax(__dsub_rn((double)lo.z, q.z), __dsub_rn(q.z, (double)hi.z)), 0.0);
-  return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-}
-
-__device__ __forceinline__ bool better(double d2, int idx, double kd2, int kidx) {
-  return d2 < kd2 || (d2 == kd2 && idx < kidx);
-}
-
-__device__ __forceinline__ void visit_leaf(const MapView& m, int leaf, const Query& q, Search& s, TopK& tk, int lane) {
-  const float4 p = __ldg(&m.pts[leaf * PLO_LEAF + lane]);
-  s.n_leaf++;
-  const double d2 = dist2(q, p.x, p.y, p.z);
-  const int cidx = __float_as_int(p.w);
-  const bool pass = (d2 <= s.r2) && (s.allow_self || d2 > DBL_EPSILON) && better(d2, cidx, s.kd2, s.kidx);
-  unsigned cand = __ballot_sync(PLO_FULL_MASK, pass);
-  while (cand) {
-    const int src = __ffs(cand) - 1;
-    cand &= cand - 1;
-    const double cd2 = __shfl_sync(PLO_FULL_MASK, d2, src);
-    const int ci = __shfl_sync(PLO_FULL_MASK, cidx, src);
-    if (!better(cd2, ci, s.kd2, s.kidx)) continue;   // warp-uniform
-    s.n_ins++;
-    const bool less = (tk.d2 < cd2) || (tk.d2 == cd2 && tk.idx < ci);
-    const int at = __popc(__ballot_sync(PLO_FULL_MASK, less) & s.kmask);
-    const double ud2 = __shfl_up_sync(PLO_FULL_MASK, tk.d2, 1);
-    const int uidx = __shfl_up_sync(PLO_FULL_MASK, tk.idx, 1);
-    const int upos = __shfl_up_sync(PLO_FULL_MASK, tk.pos, 1);
-    if (lane == at) { tk.d2 = cd2; tk.idx = ci; tk.pos = leaf * PLO_LEAF + src; }
-    else if (lane > at) { tk.d2 = ud2; tk.idx = uidx; tk.pos = upos; }
-    s.kd2 = __shfl_sync(PLO_FULL_MASK, tk.d2, s.k - 1);
-    s.kidx = __shfl_sync(PLO_FULL_MASK, tk.idx, s.k - 1);
+__device__ __forceinline__ unsigned sort32_asc(unsigned key, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const unsigned other = __shfl_xor_sync(PLO_FULL_MASK, key, j);
+      const bool up = (lane & k2) == 0;
+      const bool lower = (lane & j) == 0;
+      key = (lower == up) ? min(key, other) : max(key, other);
+    }
   }
+  return key;
 }
+
+// 32 smallest of an ascending run `best` and an ascending run `row`, ascending
+__device__ __forceinline__ unsigned merge32_low(unsigned best, unsigned row, int lane) {
+  best = min(best, __shfl_sync(PLO_FULL_MASK, row, 31 - lane));   // bitonic
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const unsigned other = __shfl_xor_sync(PLO_FULL_MASK, best, j);
+    best = ((lane & j) == 0) ? min(best, other) : max(best, other);
+  }
+  return best;
+}
+
+// sortable key of a candidate for bound purposes: rounded-up distance if the point certainly
+// satisfies libnabo's acceptance rule, else +inf
+__device__ __forceinline__ unsigned bound_key(float lo, float r2f_lo, bool allow_self) {
+  const float hi = hi_from_lo(lo);
+  const bool certain = (hi <= r2f_lo) && (allow_self || lo > 2.3e-16f);
+  return certain ? __float_as_uint(hi) : 0xffffffffu;
+}
+
+// ---- phase A: greedy bound -------------------------------------------------------------
 
 template <int LEVEL>
-struct Visit {
-  // `node` is a node of level LEVEL (or the virtual root); its children live in level LEVEL-1
-  static __device__ __forceinline__ void run(const MapView& m, int node, const Query& q, Search& s, TopK& tk, int lane) {
+struct Greedy {
+  // 32 smallest bound keys (ascending over the lanes) among the points of the kGreedyLeaves
+  // leaves nearest to q below the greedily chosen path
+  static __device__ __forceinline__ unsigned run(const MapView& m, int node, float qx, float qy, float qz, float r2f_lo,
+                                                 bool allow_self, SearchStats& st, int lane) {
     const int child = node * PLO_FANOUT + lane;
-    s.n_node++;
-    const double bd = box_dist2(q, __ldg(&m.lo[LEVEL - 1][child]), __ldg(&m.hi[LEVEL - 1][child]));
-    // positive floats order like their bit patterns; rounding down keeps the order weakly
-    const unsigned key = __float_as_uint(__double2float_rd(bd));
-    unsigned pending = PLO_FULL_MASK;
-    while (true) {
-      const double bound = fmin(s.kd2, s.r2);
-      const bool ok = ((pending >> lane) & 1u) && (bd <= bound);
-      const unsigned live = __ballot_sync(PLO_FULL_MASK, ok);
-      if (live == 0u) break;
-      const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, ok ? key : 0xffffffffu);
-      const int c = __ffs(__ballot_sync(PLO_FULL_MASK, ok && key == mn)) - 1;
-      pending &= live;            // boxes that failed once can never pass later (bound only shrinks)
-      pending &= ~(1u << c);
-      if (LEVEL == 1) visit_leaf(m, node * PLO_FANOUT + c, q, s, tk, lane);
-      else Visit<(LEVEL > 1 ? LEVEL - 1 : 1)>::run(m, node * PLO_FANOUT + c, q, s, tk, lane);
+    st.n_node++;
+    // heuristic score (any choice is valid): squared distance to the box centre
+    const float4 lo = __ldg(&m.lo[LEVEL - 1][child]), hi = __ldg(&m.hi[LEVEL - 1][child]);
+    const float cx = qx - 0.5f * (lo.x + hi.x), cy = qy - 0.5f * (lo.y + hi.y), cz = qz - 0.5f * (lo.z + hi.z);
+    const float sc = cx * cx + cy * cy + cz * cz;
+    unsigned key = (lo.x <= hi.x && sc == sc) ? __float_as_uint(fminf(sc, 3.0e38f)) : 0xffffffffu;
+    if constexpr (LEVEL == 1) {
+      unsigned best = 0xffffffffu;
+#pragma unroll 1
+      for (int t = 0; t < kGreedyLeaves; ++t) {
+        const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, key);
+        if (mn >= 0x7f800000u) break;   // no (more) non-empty leaves
+        const int c = __ffs(__ballot_sync(PLO_FULL_MASK, key == mn)) - 1;
+        if (lane == c) key = 0xffffffffu;
+        const float4 p = __ldg(&m.pts[(node * PLO_FANOUT + c) * PLO_LEAF + lane]);
+        st.n_leaf++;
+        const unsigned row = sort32_asc(bound_key(dist_lo2(qx, qy, qz, p), r2f_lo, allow_self), lane);
+        best = (t == 0) ? row : merge32_low(best, row, lane);
+      }
+      return best;
+    } else {
+      const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, key);
+      if (mn >= 0x7f800000u) return 0xffffffffu;   // only empty boxes below
+      const int c = __ffs(__ballot_sync(PLO_FULL_MASK, key == mn)) - 1;
+      return Greedy<LEVEL - 1>::run(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, allow_self, st, lane);
     }
   }
 };
 
-__device__ __forceinline__ void knn_search(const MapView& m, const Query& q, Search& s, TopK& tk, int lane) {
-  tk.d2 = CUDART_INF;
-  tk.idx = 0x7fffffff;
-  tk.pos = -1;
-  s.kd2 = CUDART_INF;
-  s.kidx = 0x7fffffff;
-  s.n_leaf = s.n_node = s.n_ins = 0;
-  if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) return;
-  switch (m.n_levels) {   // warp-uniform
-    case 1: Visit<1>::run(m, 0, q, s, tk, lane); break;
-    case 2: Visit<2>::run(m, 0, q, s, tk, lane); break;
-    case 3: Visit<3>::run(m, 0, q, s, tk, lane); break;
-    case 4: Visit<4>::run(m, 0, q, s, tk, lane); break;
-    case 5: Visit<5>::run(m, 0, q, s, tk, lane); break;
-    case 6: Visit<6>::run(m, 0, q, s, tk, lane); break;
-    default: break;
+// ---- phase C: exact distances + rank selection -----------------------------------------
+
+// ranks of the C candidates in ws.d2/ws.idx under the (d2, index) order; ranks < k are scattered:
+// afterwards ws.o*[j] is the j-th best (d2 = +inf where fewer than k are acceptable)
+__device__ __forceinline__ void rank_select(WarpScratch& ws, int C, int k, int lane) {
+  ws.od2[lane] = CUDART_INF;
+  ws.oidx[lane] = -1;
+  ws.opos[lane] = -1;
+  __syncwarp();
+  for (int base = 0; base < C; base += 64) {
+    const int i0 = base + lane, i1 = base + 32 + lane;
+    const bool own0 = i0 < C, own1 = i1 < C;
+    const double d0 = own0 ? ws.d2[i0] : CUDART_INF, d1 = own1 ? ws.d2[i1] : CUDART_INF;
+    const int x0 = own0 ? ws.idx[i0] : 0x7fffffff, x1 = own1 ? ws.idx[i1] : 0x7fffffff;
+    int r0 = 0, r1 = 0;
+    if (C - base > 32) {
+      for (int j = 0; j < C; ++j) {
+        const double dj = ws.d2[j];
+        const int ij = ws.idx[j];
+        r0 += (dj < d0 || (dj == d0 && ij < x0)) ? 1 : 0;
+        r1 += (dj < d1 || (dj == d1 && ij < x1)) ? 1 : 0;
+      }
+    } else {
+      for (int j = 0; j < C; ++j) {
+        const double dj = ws.d2[j];
+        const int ij = ws.idx[j];
+        r0 += (dj < d0 || (dj == d0 && ij < x0)) ? 1 : 0;
+      }
+    }
+    if (own0 && r0 < k && d0 < CUDART_INF) { ws.od2[r0] = d0; ws.oidx[r0] = x0; ws.opos[r0] = ws.pos[i0]; }
+    if (own1 && r1 < k && d1 < CUDART_INF) { ws.od2[r1] = d1; ws.oidx[r1] = x1; ws.opos[r1] = ws.pos[i1]; }
   }
+  __syncwarp();
+}
+
+
+// exact fp64 distances of the buffered candidates, libnabo's acceptance rule (unacceptable -> +inf)
+__device__ __forceinline__ void exact_distances(const MapView& m, WarpScratch& ws, int count, float qx, float qy, float qz,
+                                                double r2, bool allow_self, int lane) {
+  const double dqx = (double)qx, dqy = (double)qy, dqz = (double)qz;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    if (i < count) {
+      const float4 p = __ldg(&m.pts[ws.pos[i]]);
+      const double d2 = dist2_exact(dqx, dqy, dqz, p);
+      const bool ok = (d2 <= r2) && (allow_self || d2 > DBL_EPSILON);
+      ws.d2[i] = ok ? d2 : CUDART_INF;
+      ws.idx[i] = __float_as_int(p.w);
+    }
+  }
+  __syncwarp();
+}
+
+// massive ties at the bound (e.g. > 96 coincident points): keep the exact k best of the buffer.
+// Out of line: pathological inputs only.
+__device__ __noinline__ float exact_shrink(const MapView& m, WarpScratch* ws, int count, float qx, float qy, float qz, double r2,
+                                           int allow_self, int k, float Df) {
+  const int lane = threadIdx.x & 31;
+  exact_distances(m, *ws, count, qx, qy, qz, r2, allow_self != 0, lane);
+  rank_select(*ws, count, k, lane);
+  if (lane < k) {
+    ws->pos[lane] = ws->opos[lane];
+    ws->lo[lane] = (ws->od2[lane] < CUDART_INF) ? __double2float_rd(ws->od2[lane]) : CUDART_INF_F;
+  }
+  const double kd = ws->od2[k - 1];
+  __syncwarp();
+  return (kd < CUDART_INF) ? fminf(Df, bound_f(kd)) : Df;
+}
+
+// ---- phase B: conservative collect -----------------------------------------------------
+
+struct Collector {
+  float Df;       // current float threshold for lower bounds (warp-uniform)
+  int count;      // buffered candidates
+  int appended;   // statistics
+  int shrinks;
+};
+
+// buffer full: Df <- k-th smallest rounded-up distance among the buffered candidates that are
+// certainly acceptable; buffer compacted to lo <= Df.  Out of line: rare.
+__device__ __noinline__ int shrink_buffer(WarpScratch* ws, int count, float* Df_io, float r2f_lo, int allow_self, int k) {
+  const int lane = threadIdx.x & 31;
+  unsigned best = 0xffffffffu;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    const unsigned key = (i < count) ? bound_key(ws->lo[i], r2f_lo, allow_self != 0) : 0xffffffffu;
+    const unsigned row = sort32_asc(key, lane);
+    best = (base == 0) ? row : merge32_low(best, row, lane);
+  }
+  float Df = *Df_io;
+  const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
+  if (kth < 0x7f800000u) Df = fminf(Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
+  int kept = 0;
+  for (int base = 0; base < count; base += 32) {   // in-place stable compaction (o <= i)
+    const int i = base + lane;
+    float l = 0.f;
+    int ps = 0;
+    bool keepit = false;
+    if (i < count) { l = ws->lo[i]; ps = ws->pos[i]; keepit = l <= Df; }
+    const unsigned b = __ballot_sync(PLO_FULL_MASK, keepit);
+    __syncwarp();
+    if (keepit) {
+      const int o = kept + __popc(b & ((1u << lane) - 1u));
+      ws->lo[o] = l;
+      ws->pos[o] = ps;
+    }
+    kept += __popc(b);
+    __syncwarp();
+  }
+  *Df_io = Df;
+  return kept;
+}
+
+__device__ __forceinline__ void collect_leaf(const MapView& m, int leaf, float qx, float qy, float qz, float r2f_lo, double r2,
+                                             bool allow_self, int k, WarpScratch& ws, Collector& col, SearchStats& st,
+                                             int lane) {
+  const float4 p = __ldg(&m.pts[leaf * PLO_LEAF + lane]);
+  st.n_leaf++;
+  const float lo = dist_lo2(qx, qy, qz, p);
+  bool pass = lo <= col.Df;
+  unsigned b = __ballot_sync(PLO_FULL_MASK, pass);
+  if (b == 0u) return;
+  if (col.count + __popc(b) > kCap) {
+    float Df = col.Df;
+    col.count = shrink_buffer(&ws, col.count, &Df, r2f_lo, allow_self ? 1 : 0, k);
+    col.Df = Df;
+    col.shrinks++;
+    pass = pass && (lo <= col.Df);
+    b = __ballot_sync(PLO_FULL_MASK, pass);
+    if (col.count + __popc(b) > kCap) {   // still full: > kCap - 32 candidates tie at the bound
+      col.Df = exact_shrink(m, &ws, col.count, qx, qy, qz, r2, allow_self ? 1 : 0, k, col.Df);
+      col.count = k;   // entries with d2 = +inf among them are dropped again by phase C
+      col.shrinks += 1000;
+      pass = pass && (lo <= col.Df);
+      b = __ballot_sync(PLO_FULL_MASK, pass);
+    }
+    if (b == 0u) return;
+  }
+  if (pass) {
+    const int o = col.count + __popc(b & ((1u << lane) - 1u));
+    ws.lo[o] = lo;
+    ws.pos[o] = leaf * PLO_LEAF + lane;
+  }
+  col.count += __popc(b);
+  col.appended += __popc(b);
+}
+
+template <int LEVEL>
+struct Collect {
+  static __device__ __forceinline__ void run(const MapView& m, int node, float qx, float qy, float qz, float r2f_lo, double r2,
+                                             bool allow_self, int k, WarpScratch& ws, Collector& col, SearchStats& st,
+                                             int lane) {
+    const int child = node * PLO_FANOUT + lane;
+    st.n_node++;
+    const float4 lo = __ldg(&m.lo[LEVEL - 1][child]), hi = __ldg(&m.hi[LEVEL - 1][child]);
+    const float bd = box_lo2(qx, qy, qz, lo, hi);
+    // visiting order (any order is exact): nearest box centre first, so that a loose bound is
+    // tightened by the densest neighbourhood of q as early as possible
+    const float cx = qx - 0.5f * (lo.x + hi.x), cy = qy - 0.5f * (lo.y + hi.y), cz = qz - 0.5f * (lo.z + hi.z);
+    const unsigned key = __float_as_uint(fminf(cx * cx + cy * cy + cz * cz, 3.0e38f));
+    unsigned mask = __ballot_sync(PLO_FULL_MASK, bd <= col.Df);
+    int shrinks_seen = col.shrinks;
+    while (mask != 0u) {
+      int c;
+      if ((mask & (mask - 1)) == 0u) c = __ffs(mask) - 1;   // single child left
+      else {
+        const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) ? key : 0xffffffffu);
+        c = __ffs(__ballot_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) && key == mn)) - 1;
+      }
+      mask &= ~(1u << c);
+      if constexpr (LEVEL == 1) collect_leaf(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+      else Collect<LEVEL - 1>::run(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+      if (col.shrinks != shrinks_seen) {   // the bound shrank below: re-test the remaining children
+        shrinks_seen = col.shrinks;
+        mask &= __ballot_sync(PLO_FULL_MASK, bd <= col.Df);
+      }
+    }
+  }
+};
+
+// exact k-NN of q (float32 coordinates, as the reference stores the transformed point).
+// D0: a proven upper bound of the k-th distance (squared) or +inf; with `refine` the greedy
+// bound is evaluated as well.  Result: lane j holds neighbour j (d2 = +inf where not filled).
+template <int LEVELS>
+__device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, float qz, double D0, bool refine, double r2,
+                                         int k, bool allow_self, WarpScratch& ws, TopK& tk, SearchStats& st, int lane) {
+  st.n_leaf = st.n_node = st.n_cand = 0;
+  tk.d2 = CUDART_INF;
+  tk.idx = -1;
+  tk.pos = -1;
+  if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) return;
+  const float r2f_lo = __double2float_rd(r2);   // "certainly within the radius" threshold
+  Collector col;
+  col.Df = bound_f(fmin(D0, r2));
+  if (refine || !(D0 < r2)) {
+    const unsigned best = Greedy<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, allow_self, st, lane);
+    const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
+    if (kth < 0x7f800000u) col.Df = fminf(col.Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
+  }
+  col.count = 0;
+  col.appended = 0;
+  col.shrinks = 0;
+  Collect<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+  __syncwarp();
+  st.n_cand = col.appended + 100000 * col.shrinks;
+  exact_distances(m, ws, col.count, qx, qy, qz, r2, allow_self, lane);
+  rank_select(ws, col.count, k, lane);
+  tk.d2 = ws.od2[lane];
+  tk.idx = ws.oidx[lane];
+  tk.pos = ws.opos[lane];
+  __syncwarp();
+}
+
+// the rare second search of the 1-NN rule (k = 1, no self match), out of line; result in ws.o*[0]
+template <int LEVELS>
+__device__ __noinline__ void knn1_noself(const MapView& m, float qx, float qy, float qz, double r2, WarpScratch* ws) {
+  TopK tk;
+  SearchStats st;
+  knn_topk<LEVELS>(m, qx, qy, qz, CUDART_INF, true, r2, 1, false, *ws, tk, st, threadIdx.x & 31);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -145,15 +396,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ bool finite3d(double a, double b, double c) { return isfinite(a) && isfinite(b) && isfinite(c); }
 
 // `angle > thr` of src/imls_icp.cpp:444-451 / :683-692, NaN => false (point kept).
-// Decided on the cosine when it is clearly away from the threshold, by acos otherwise.
+// A float estimate of the cosine (rel. error < 1e-6) decides when it is more than 1e-5 away
+// from cos(thr); otherwise the reference's own formula (sqrt, divide, acos in double) does.
 __device__ __forceinline__ bool angle_exceeds(double ax, double ay, double az, double bx, double by, double bz,
                                               const DevParams& P) {
   const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
-  const double na = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
-  const double nb = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz)));
-  const double c = dot / (na * nb);
+  const double na2 = __dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az));
+  const double nb2 = __dadd_rn(__dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by)), __dmul_rn(bz, bz));
+  const float prod = (float)(na2 * nb2);
+  if (prod > 1e-30f && prod < 1e30f) {
+    const float ce = (float)dot * rsqrtf(prod);
+    if (fabsf(ce) < 0.999f && fabsf(ce - (float)P.cos_thr) > 1e-5f) return ce < (float)P.cos_thr;
+  }
+  const double c = dot / (sqrt(na2) * sqrt(nb2));
   if (!(c == c)) return false;
-  if (fabs(c - P.cos_thr) > 1e-9 && fabs(c) <= 1.0) return c < P.cos_thr;
   const double angle = acos(c) * 180.0 / 3.14159265358979323846;
   return angle > P.angle_thr;
 }
@@ -163,22 +419,28 @@ struct ProjectOut {
   float4* qy;        // projected point y (float32)
   float4* qn;        // normal of the 1-NN (float32)
   int* status;
+  double* kd2;       // k-th neighbour distance of this projection (+inf if the list is not full)
   // hooks
   double* height;
   int* nn1_idx;
   double* nn1_d2;
   int* nn_idx;
   double* nn_d2;
-  int* search_stats;   // [M*3] leaves, internal nodes, insertions of the k-NN search
+  int* search_stats;   // [M*3] leaves scanned, nodes expanded, candidates buffered (+ 100000 * shrinks)
 };
 
-template <bool PCA>
-__global__ void __launch_bounds__(256) k_project(MapView m, const float4* __restrict__ sp, const float4* __restrict__ sn,
-                                                 const DevCounts* __restrict__ counts, const DevState* __restrict__ st,
-                                                 DevParams P, ProjectOut out, int hooks) {
+template <bool PCA, int LEVELS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const __grid_constant__ MapView m,
+                                                                          const float4* __restrict__ sp,
+                                                                          const float4* __restrict__ sn,
+                                                                          const DevCounts* __restrict__ counts,
+                                                                          const DevState* __restrict__ st, DevParams P,
+                                                                          ProjectOut out, int hooks, int use_prev, int chunk,
+                                                                          int* __restrict__ chunk_counter) {
   if (st->done) return;
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
   const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
   // rPose rows (src/laser_odometry.cpp:530-535)
@@ -186,7 +448,17 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
 #pragma unroll
   for (int i = 0; i < 12; ++i) T[i] = st->rPose[i];
 
-  for (int qi = blockIdx.x * wpb + (threadIdx.x >> 5); qi < n_src; qi += gridDim.x * wpb) {
+  // Each warp walks chunks of `chunk` consecutive source points (handed out dynamically, one
+  // atomic per chunk: per-query cost varies a lot).  Correctness never depends on the order of
+  // the source points, only the quality of the carry bound does.
+  while (true) {
+   int c0 = 0;
+   if (lane == 0) c0 = atomicAdd(chunk_counter, 1) * chunk;
+   c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+   if (c0 >= n_src) break;
+   double carry_kd2 = CUDART_INF, carry_x = 0.0, carry_y = 0.0, carry_z = 0.0;
+   const int c1 = min(c0 + chunk, n_src);
+   for (int qi = c0; qi < c1; ++qi) {
     const float4 p = __ldg(&sp[qi]);
     const float4 nf = __ldg(&sn[qi]);
     const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
@@ -201,18 +473,41 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
       nyf = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], cc)));
       nzf = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], cc)));
     }
-    Query q{(double)xf, (double)yf, (double)zf};           // imls_icp.cpp:556
+    const double qx = (double)xf, qy = (double)yf, qz = (double)zf;        // imls_icp.cpp:556
     const double xnx = (double)nxf, xny = (double)nyf, xnz = (double)nzf;   // :557
 
-    Search s;
-    s.r2 = P.r2;
-    s.k = P.k;
-    s.kmask = (P.k >= 32) ? 0xffffffffu : ((1u << P.k) - 1u);
-    s.allow_self = true;   // :372-375 ALLOW_SELF_MATCH
+    // bounds of the k-th distance by the triangle inequality: the k points that were nearest to a
+    // reference position x_ref are all within sqrt(kd2_ref) + |x - x_ref| of x.  Reference =
+    // this query in the previous projection (temporal) and the previous query of the chunk (carry).
+    double D0 = CUDART_INF, ref_kd2 = CUDART_INF;
+    if (use_prev) {
+      const double kprev = out.kd2[qi];
+      if (kprev < CUDART_INF) {
+        const float4 xp = out.qx[qi];
+        const double ex = qx - (double)xp.x, ey = qy - (double)xp.y, ez = qz - (double)xp.z;
+        const double rad = sqrt(kprev) + sqrt(ex * ex + ey * ey + ez * ez);
+        D0 = rad * rad * (1.0 + 1e-9);
+        ref_kd2 = kprev;
+      }
+    }
+    if (carry_kd2 < CUDART_INF) {
+      const double ex = qx - carry_x, ey = qy - carry_y, ez = qz - carry_z;
+      const double rad = sqrt(carry_kd2) + sqrt(ex * ex + ey * ey + ez * ez);
+      const double Dc = rad * rad * (1.0 + 1e-9);
+      if (Dc < D0) { D0 = Dc; ref_kd2 = carry_kd2; }
+    }
+    if (!(D0 == D0)) D0 = CUDART_INF;
+    // a bound more than 2.5x (in distance) above its reference would buffer > 6x k candidates:
+    // evaluate the greedy bound as well
+    const bool refine = !(D0 <= 6.25 * ref_kd2);
+
     TopK tk;
-    if (n_tgt > 0) knn_search(m, q, s, tk, lane);
-    else { tk.d2 = CUDART_INF; tk.idx = 0x7fffffff; tk.pos = -1; s.n_leaf = s.n_node = s.n_ins = 0; }
+    SearchStats ss;
+    if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, D0, refine, P.r2, P.k, true, ws, tk, ss, lane);   // :372-375 ALLOW_SELF_MATCH
+    else { tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1; ss.n_leaf = ss.n_node = ss.n_cand = 0; }
     const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
+    const double kd2_now = __shfl_sync(PLO_FULL_MASK, tk.d2, P.k - 1);
+    carry_kd2 = kd2_now; carry_x = qx; carry_y = qy; carry_z = qz;
 
     // ---- 1-NN without self match (:601-609) ----
     int i1 = -1, pos1 = -1;
@@ -226,16 +521,10 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
         d1 = __shfl_sync(PLO_FULL_MASK, tk.d2, j1);
       } else if (__popc(__ballot_sync(PLO_FULL_MASK, has)) == P.k) {
         // the list is full of points coincident with the query: search again, k = 1, no self match
-        Search s1;
-        s1.r2 = P.r2; s1.k = 1; s1.kmask = 1u; s1.allow_self = false;
-        TopK t1;
-        knn_search(m, q, s1, t1, lane);
-        const double dd = __shfl_sync(PLO_FULL_MASK, t1.d2, 0);
-        if (dd < CUDART_INF) {
-          d1 = dd;
-          i1 = __shfl_sync(PLO_FULL_MASK, t1.idx, 0);
-          pos1 = __shfl_sync(PLO_FULL_MASK, t1.pos, 0);
-        }
+        knn1_noself<LEVELS>(m, xf, yf, zf, P.r2, &ws);
+        const double dd = ws.od2[0];
+        if (dd < CUDART_INF) { d1 = dd; i1 = ws.oidx[0]; pos1 = ws.opos[0]; }
+        __syncwarp();
       }
     }
 
@@ -246,7 +535,7 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
       const float4 pp = __ldg(&m.pts[tk.pos]);
       if (PCA) { pnx = m.nrm_pca[3 * (size_t)tk.pos]; pny = m.nrm_pca[3 * (size_t)tk.pos + 1]; pnz = m.nrm_pca[3 * (size_t)tk.pos + 2]; }
       else { const float4 nn = __ldg(&m.nrm[tk.pos]); pnx = (double)nn.x; pny = (double)nn.y; pnz = (double)nn.z; }
-      ddx = __dsub_rn(q.x, (double)pp.x); ddy = __dsub_rn(q.y, (double)pp.y); ddz = __dsub_rn(q.z, (double)pp.z);
+      ddx = __dsub_rn(qx, (double)pp.x); ddy = __dsub_rn(qy, (double)pp.y); ddz = __dsub_rn(qz, (double)pp.z);
       keep = finite3d(pnx, pny, pnz);                                           // :436-440 (:396-400 holds by construction)
       if (keep && P.angle_constraint) keep = !angle_exceeds(xnx, xny, xnz, pnx, pny, pnz, P);   // :442-451
     }
@@ -266,11 +555,12 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
       const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, keep));
       if (cnt < 3) status = PLO_PT_MLS_FAIL;               // :463-466, :696-701
       else {
-        // :468 — the bandwidth indexes the UNFILTERED sorted distance list with the filtered count
-        const double hmax = sqrt(__shfl_sync(PLO_FULL_MASK, tk.d2, cnt - 1)) / 3.0;
+        // :468 — the bandwidth h_max = sqrt(d2[cnt-1]) / 3 indexes the UNFILTERED sorted distance
+        // list with the filtered count; -d2 / h_max / h_max == -9 * d2 / d2[cnt-1]
+        const double cinv = -9.0 / __shfl_sync(PLO_FULL_MASK, tk.d2, cnt - 1);
         double w = 0.0, pr = 0.0;
         if (keep) {
-          w = exp(-tk.d2 / hmax / hmax);                   // :474-475 (diff_norm == d2, same arithmetic)
+          w = exp(tk.d2 * cinv);                           // :474-475 (diff_norm == d2, same arithmetic)
           pr = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(w, ddx), pnx), __dmul_rn(__dmul_rn(w, ddy), pny)), __dmul_rn(__dmul_rn(w, ddz), pnz));   // :476
         }
         const double wsum = warp_sum(w), psum = warp_sum(pr);
@@ -282,13 +572,14 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
       float4 ox = make_float4(xf, yf, zf, __int_as_float(status));
       float4 oy = make_float4(0.f, 0.f, 0.f, 0.f), on = make_float4(0.f, 0.f, 0.f, 0.f);
       if (status == PLO_PT_OK) {   // :719-731
-        oy.x = __double2float_rn(__dsub_rn(q.x, __dmul_rn(height, n0x)));
-        oy.y = __double2float_rn(__dsub_rn(q.y, __dmul_rn(height, n0y)));
-        oy.z = __double2float_rn(__dsub_rn(q.z, __dmul_rn(height, n0z)));
+        oy.x = __double2float_rn(__dsub_rn(qx, __dmul_rn(height, n0x)));
+        oy.y = __double2float_rn(__dsub_rn(qy, __dmul_rn(height, n0y)));
+        oy.z = __double2float_rn(__dsub_rn(qz, __dmul_rn(height, n0z)));
         on.x = __double2float_rn(n0x); on.y = __double2float_rn(n0y); on.z = __double2float_rn(n0z);
       }
       out.qx[qi] = ox; out.qy[qi] = oy; out.qn[qi] = on;
       out.status[qi] = status;
+      out.kd2[qi] = kd2_now;
     }
     if (hooks) {
       if (lane < P.k) {
@@ -299,11 +590,12 @@ __global__ void __launch_bounds__(256) k_project(MapView m, const float4* __rest
         out.height[qi] = height;
         out.nn1_idx[qi] = i1;
         out.nn1_d2[qi] = d1;
-        out.search_stats[3 * (size_t)qi] = s.n_leaf;
-        out.search_stats[3 * (size_t)qi + 1] = s.n_node;
-        out.search_stats[3 * (size_t)qi + 2] = s.n_ins;
+        out.search_stats[3 * (size_t)qi] = ss.n_leaf;
+        out.search_stats[3 * (size_t)qi + 1] = ss.n_node;
+        out.search_stats[3 * (size_t)qi + 2] = ss.n_cand;
       }
     }
+   }
   }
 }
 
@@ -340,29 +632,30 @@ __device__ void smallest_eigvec3(double a00, double a01, double a02, double a11,
 
 // one warp per map point (sorted position): k_normal nearest within r_normal, no self
 // match (flags = SORT_RESULTS only, :414-416); D1: a normal exists iff all slots filled.
-__global__ void __launch_bounds__(256) k_pca_normals(MapView m, DevParams P, double* __restrict__ nrm_pca, int n_pad) {
+template <int LEVELS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_pca_normals(const __grid_constant__ MapView m, DevParams P,
+                                                                    double* __restrict__ nrm_pca, int n_pad) {
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
+  WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int pos = blockIdx.x * wpb + (threadIdx.x >> 5); pos < n_pad; pos += gridDim.x * wpb) {
     const float4 p = __ldg(&m.pts[pos]);
     double nx = CUDART_INF, ny = CUDART_INF, nz = CUDART_INF;   // :418-421
     if (isfinite(p.x)) {
-      Query q{(double)p.x, (double)p.y, (double)p.z};
-      Search s;
-      s.r2 = P.r_normal2; s.k = P.k_normal; s.kmask = (P.k_normal >= 32) ? 0xffffffffu : ((1u << P.k_normal) - 1u);
-      s.allow_self = false;
       TopK tk;
-      knn_search(m, q, s, tk, lane);
+      SearchStats ss;
+      knn_topk<LEVELS>(m, p.x, p.y, p.z, CUDART_INF, true, P.r_normal2, P.k_normal, false, ws, tk, ss, lane);
       const bool has = (lane < P.k_normal) && (tk.d2 < CUDART_INF);
       const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, has));
       if (cnt == P.k_normal) {
         double x = 0.0, y = 0.0, z = 0.0;
         if (has) { const float4 pp = __ldg(&m.pts[tk.pos]); x = (double)pp.x; y = (double)pp.y; z = (double)pp.z; }
-        const double inv = 1.0 / (double)cnt;
-        const double mx = warp_sum(x) * inv, my = warp_sum(y) * inv, mz = warp_sum(z) * inv;   // :758-763
+        const double nd = (double)cnt;
+        const double mx = warp_sum(x) / nd, my = warp_sum(y) / nd, mz = warp_sum(z) / nd;   // :758-763
         const double dx = has ? x - mx : 0.0, dy = has ? y - my : 0.0, dz = has ? z - mz : 0.0;
-        const double c00 = warp_sum(dx * dx) * inv, c01 = warp_sum(dx * dy) * inv, c02 = warp_sum(dx * dz) * inv;   // :766-771
-        const double c11 = warp_sum(dy * dy) * inv, c12 = warp_sum(dy * dz) * inv, c22 = warp_sum(dz * dz) * inv;
+        const double c00 = warp_sum(dx * dx) / nd, c01 = warp_sum(dx * dy) / nd, c02 = warp_sum(dx * dz) / nd;   // :766-771
+        const double c11 = warp_sum(dy * dy) / nd, c12 = warp_sum(dy * dz) / nd, c22 = warp_sum(dz * dz) / nd;
         double v[3];
         smallest_eigvec3(c00, c01, c02, c11, c12, c22, v);   // :776-778
         const double nn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
@@ -387,6 +680,7 @@ int plo_reserve_query_buffers(plo_ctx* c, bool hooks) {
   PLO_CUDA(c, c->q_y.reserve(sizeof(float4) * m));
   PLO_CUDA(c, c->q_n.reserve(sizeof(float4) * m));
   PLO_CUDA(c, c->q_status.reserve(sizeof(int) * m));
+  PLO_CUDA(c, c->q_kd2.reserve(sizeof(double) * m));
   if (hooks) {
     PLO_CUDA(c, c->q_height.reserve(sizeof(double) * m));
     PLO_CUDA(c, c->q_nn1_idx.reserve(sizeof(int) * m));
@@ -401,29 +695,67 @@ int plo_reserve_query_buffers(plo_ctx* c, bool hooks) {
 int plo_launch_pca_normals(plo_ctx* c) {
   if (c->pca_valid || c->n_raw_t == 0) { c->pca_valid = true; return PLO_OK; }
   PLO_CUDA(c, c->nrm_pca.reserve(sizeof(double) * 3 * (size_t)c->n_pad_t));
-  k_pca_normals<<<plo_grid(c, 8), 256, 0, c->stream>>>(c->map_view(), c->dprm, c->nrm_pca.as<double>(), (int)c->n_pad_t);
+  const int grid = plo_grid(c, 4);
+  const MapView mv = c->map_view();
+  double* out = c->nrm_pca.as<double>();
+  switch (c->n_levels) {
+    case 1: k_pca_normals<1><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 2: k_pca_normals<2><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 3: k_pca_normals<3><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 4: k_pca_normals<4><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 5: k_pca_normals<5><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    default: k_pca_normals<6><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+  }
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   c->pca_valid = true;
   return PLO_OK;
 }
 
+namespace {
+template <bool PCA>
+void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int hooks, int chunk) {
+  const MapView mv = c->map_view();
+  const float4* sp = c->s_p.as<float4>();
+  const float4* sn = c->s_n.as<float4>();
+  const DevCounts* dc = c->counts.as<DevCounts>();
+  const DevState* st = c->state.as<DevState>();
+  int* cc = c->chunk_counter.as<int>();
+  const int up = c->prev_valid ? 1 : 0;
+  const int T = kWarpsPerBlock * 32;
+  switch (c->n_levels) {   // an empty map (n_levels == 0) never walks the tree: any instantiation does
+    case 0:
+    case 1: k_project<PCA, 1><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    case 2: k_project<PCA, 2><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    case 3: k_project<PCA, 3><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    case 4: k_project<PCA, 4><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    case 5: k_project<PCA, 5><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    default: k_project<PCA, 6><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+  }
+}
+}  // namespace
+
 int plo_launch_project(plo_ctx* c, bool hooks) {
   if (c->m_raw == 0) return PLO_OK;
   ProjectOut out;
   out.qx = c->q_x.as<float4>(); out.qy = c->q_y.as<float4>(); out.qn = c->q_n.as<float4>();
   out.status = c->q_status.as<int>();
+  out.kd2 = c->q_kd2.as<double>();
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
   out.search_stats = c->q_stats.as<int>();
-  const int64_t warps = c->m_raw;
-  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)plo_grid(c, 8)));
-  if (c->dprm.use_pca_normals)
-    k_project<true><<<blocks, 256, 0, c->stream>>>(c->map_view(), c->s_p.as<float4>(), c->s_n.as<float4>(),
-                                                   c->counts.as<DevCounts>(), c->state.as<DevState>(), c->dprm, out, hooks ? 1 : 0);
-  else
-    k_project<false><<<blocks, 256, 0, c->stream>>>(c->map_view(), c->s_p.as<float4>(), c->s_n.as<float4>(),
-                                                    c->counts.as<DevCounts>(), c->state.as<DevState>(), c->dprm, out, hooks ? 1 : 0);
+  // chunk length: up to 4 consecutive queries per warp, fewer when the cloud is too small to fill
+  // the GPU; persistent grid (PLO_MINB blocks per SM), chunks fetched through an atomic counter
+  const int64_t slots = (int64_t)plo_grid(c, PLO_MINB) * kWarpsPerBlock;
+  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(4, c->m_raw / (2 * slots)));
+  if (const char* e = getenv("PLO_CHUNK")) chunk = std::max(1, atoi(e));   // tuning knob
+  const int64_t warps = (c->m_raw + chunk - 1) / chunk;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
+  PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
+  PLO_CUDA(c, cudaMemsetAsync(c->chunk_counter.p, 0, sizeof(int), c->stream));
+  if (c->dprm.use_pca_normals) launch_project_levels<true>(c, blocks, out, hooks ? 1 : 0, chunk);
+  else launch_project_levels<false>(c, blocks, out, hooks ? 1 : 0, chunk);
+  c->prev_valid = true;   // later projections of the same clouds may use this one's k-th distances
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;

@@ -111,13 +111,14 @@ struct plo_ctx {
   DevBuf s_stage, s_praw, s_nraw, s_p, s_n;
 
   // per-query results of the last projection
-  DevBuf q_x, q_y, q_n, q_status;
+  DevBuf q_x, q_y, q_n, q_status, q_kd2;
+  bool prev_valid = false;   // q_x / q_kd2 hold the previous projection of the SAME clouds and k, r
   bool hooks_valid = false;
   DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2, q_stats;
   bool projected = false;
 
   // reduction / solve
-  DevBuf partials, state, counts, scratch;
+  DevBuf partials, state, counts, scratch, chunk_counter;
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
   DevState* h_state = nullptr;       // pinned
   DevCounts* h_counts = nullptr;     // pinned

@@ -164,6 +164,29 @@ def test_ties_duplicates_and_self_match(oracle_mod):
     assert o["nn1_idx"][0] >= 40
 
 
+def test_massive_ties_fill_the_candidate_buffer(oracle_mod):
+    # hundreds of coincident / equidistant points around a query overflow the per-warp candidate
+    # buffer: exercises the bound-shrink and the exact tie-resolution paths of the collect phase
+    rng = np.random.default_rng(1)
+    tgt = np.zeros((3000, 12), np.float32)
+    tgt[:, 6] = 1
+    tgt[:300, 0:3] = [1, 1, 1]
+    th = rng.uniform(0, 2 * np.pi, 700)
+    tgt[300:1000, 0] = 1 + 0.5 * np.cos(th)
+    tgt[300:1000, 1] = 1 + 0.5 * np.sin(th)
+    tgt[300:1000, 2] = 1
+    tgt[1000:, 0:3] = rng.uniform(-3, 5, size=(2000, 3))
+    src = np.zeros((4, 12), np.float32)
+    src[:, 6] = 1
+    src[0, 0:3] = [1, 1, 1]
+    src[1, 0:3] = [1, 1, 1.001]
+    src[2, 0:3] = [1.2, 1, 1]
+    for k in (20, 32, 3):
+        ctx, orc = _both(oracle_mod, tgt, src, search_number=k)
+        _check_projection(ctx, orc)
+        assert (ctx.search_stats()[:, 2] >= 100000).any()      # at least one query shrank its buffer
+
+
 def test_each_drop_reason_on_gpu(oracle_mod):
     rng = np.random.default_rng(11)
     tgt = np.zeros((3000, 12), np.float32)

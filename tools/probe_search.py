@@ -21,3 +21,11 @@ T, rs = ctx.register()
 print("register", rs["iters"], rs["status_name"], ctx.last_timings())
 for T_ in (np.eye(4), T):
     print("k_project ms", ctx.time_project_kernel(T_, reps))
+fb = (ss[:, 2] < 0).mean()
+print("fallback fraction at iteration 0:", fb, " collected mean (non-fallback):", ss[ss[:, 2] >= 0, 2].mean() if (ss[:, 2] >= 0).any() else None)
+ctx.set_target(pair.target); ctx.set_source(pair.source)
+import time
+for _ in range(3):
+    ctx.set_target(pair.target); ctx.set_source(pair.source); T, rs = ctx.register(); print(ctx.last_timings())
+ctx.project(T, hooks=True); ss2 = ctx.search_stats()
+print("converged-pose stats: leaves %.2f nodes %.2f cand %.2f fallback %.4f" % (ss2[:,0].mean(), ss2[:,1].mean(), ss2[ss2[:,2]>=0,2].mean(), (ss2[:,2]<0).mean()))
