@@ -1,0 +1,192 @@
+/*
+ * imls_icp_cuda.h — C++ adapter over plo_c_api.h that mirrors the reference's matcher and
+ * solver surface, so that src/laser_odometry.cpp can switch back-ends by changing two type /
+ * function names:
+ *
+ *   class IMLSICPMatcherCUDA            <->  class IMLSICPMatcher   (include/imls_icp.h:45-147)
+ *   SolveMotionEstimationProblemWeightedLS_CUDA
+ *                                       <->  SolveMotionEstimationProblemWeightedLS
+ *                                            (include/solver.h:92-98, src/solver.cpp:168-220)
+ *
+ * Header-only, C++11, no dependency beyond the C ABI: it is templated on the point / vector /
+ * matrix types so that it compiles here without PCL / Eigen and, in the reference tree, with
+ * pcl::PointCloud<pcl::PointXYZINormal> and Eigen::Vector3d / Eigen::Matrix4d.
+ *
+ * Requirements on the template arguments
+ *   PointT  : trivially copyable record, float x,y,z at byte 0 and float normal_x/y/z at byte 16
+ *             (pcl::PointXYZINormal, 48 bytes — include/common.h:17)
+ *   CloudT  : has `.points` (contiguous std::vector<PointT>-like: data(), size(), resize(), clear())
+ *   Vec3T   : operator()(int) or operator[](int) giving double components (Eigen::Vector3d)
+ *   Mat4T   : operator()(row, col) assignable double (Eigen::Matrix4d)
+ *
+ * Behavioural differences from the reference that the boundary forces:
+ *   - ProjSourcePtToSurface does not erase from a caller-owned shared cloud behind the caller's
+ *     back: it rewrites `in_cloud` with the surviving (transformed) points, exactly what the
+ *     reference's in-place erase leaves there, and fills `out_cloud`; `srcIndices()` tells which
+ *     source points survived.
+ *   - The per-iteration source transform (src/laser_odometry.cpp:527-549) is done on the device:
+ *     pass the current rPose instead of a pre-transformed copy of the cloud.
+ *   - Errors throw std::runtime_error with plo_last_error() (the reference only prints).
+ */
+#ifndef PLO_IMLS_ICP_CUDA_H
+#define PLO_IMLS_ICP_CUDA_H
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "plo/plo_c_api.h"
+
+namespace plo {
+
+inline void check(plo_ctx* ctx, int rc, const char* what) {
+  if (rc != PLO_OK) throw std::runtime_error(std::string(what) + ": " + plo_last_error(ctx));
+}
+
+template <typename PointT>
+class IMLSICPMatcherCUDA {
+  static_assert(sizeof(PointT) >= 28, "PointT must hold xyz at byte 0 and a normal at byte 16");
+
+ public:
+  explicit IMLSICPMatcherCUDA(int device = 0) : ctx_(nullptr) {
+    int rc = plo_create(device, &ctx_);
+    if (rc != PLO_OK) throw std::runtime_error(std::string("plo_create: ") + plo_last_error(nullptr));
+    plo_default_params(&params_);
+  }
+  ~IMLSICPMatcherCUDA() { plo_destroy(ctx_); }
+  IMLSICPMatcherCUDA(const IMLSICPMatcherCUDA&) = delete;
+  IMLSICPMatcherCUDA& operator=(const IMLSICPMatcherCUDA&) = delete;
+
+  /* include/imls_icp.h:56, src/imls_icp.cpp:74-78 */
+  template <typename CloudPtr>
+  void setSourcePointCloud(const CloudPtr& cloud) {
+    check(ctx_, plo_set_source(ctx_, cloud->points.data(), (int64_t)cloud->points.size(), (int32_t)sizeof(PointT)),
+          "setSourcePointCloud");
+  }
+  /* include/imls_icp.h:58, src/imls_icp.cpp:80-103 */
+  template <typename CloudPtr>
+  void setTargetPointCloud(const CloudPtr& cloud) {
+    check(ctx_, plo_set_target(ctx_, cloud->points.data(), (int64_t)cloud->points.size(), (int32_t)sizeof(PointT)),
+          "setTargetPointCloud");
+  }
+
+  /* include/imls_icp.h:62-66, src/imls_icp.cpp:146-168 — same 16 arguments, same order */
+  void setParameters(int _iter, double _h, double _r, double _r_normal, double /*_r_proj*/, bool _useTensorVoting,
+                     bool _isGetNormals, bool _useProjectedDistance, int /*_tensor_k*/, double /*_tensor_sigma*/,
+                     double /*_tensor_distance_threshold*/, int _search_number_normal, int _search_number,
+                     bool _normal_angle_constraint, double _angle_diff_threshold, const std::string& /*_output_dir*/) {
+    if (_useTensorVoting) throw std::runtime_error("use_tensor_voting: out of scope of the CUDA path");
+    if (_useProjectedDistance) throw std::runtime_error("use_projected_distance: out of scope of the CUDA path");
+    params_.iterations = _iter;
+    params_.h = _h;
+    params_.r = _r;
+    params_.r_normal = _r_normal;
+    params_.is_get_normals = _isGetNormals ? 1 : 0;
+    params_.search_number_normal = _search_number_normal;
+    params_.search_number = _search_number;
+    params_.normal_angle_constraint = _normal_angle_constraint ? 1 : 0;
+    params_.angle_diff_threshold = _angle_diff_threshold;
+    check(ctx_, plo_set_params(ctx_, &params_), "setParameters");
+  }
+  /* driver-loop keys of config.json that the reference reads inside its loop
+   * (src/laser_odometry.cpp:570,606,640-641, laser_odometry.transform_normal :458) */
+  void setLoopParameters(bool transform_normal, int correspond_number, double delta_dist_threshold,
+                         double delta_angle_threshold, int weight_mode = PLO_W_UNIT) {
+    params_.transform_normal = transform_normal ? 1 : 0;
+    params_.correspond_number = correspond_number;
+    params_.delta_dist_threshold = delta_dist_threshold;
+    params_.delta_angle_threshold = delta_angle_threshold;
+    params_.weight_mode = weight_mode;
+    check(ctx_, plo_set_params(ctx_, &params_), "setLoopParameters");
+  }
+
+  /* include/imls_icp.h:79-82, src/imls_icp.cpp:496-745 (+ the transform of
+   * src/laser_odometry.cpp:527-549).  in_cloud <- surviving transformed source points,
+   * out_cloud <- projected points y with the matched normal; counters as printed at :736-744. */
+  template <typename CloudPtr, typename Mat4T>
+  void ProjSourcePtToSurface(const Mat4T& rPose, CloudPtr& in_cloud, CloudPtr& out_cloud, const std::string& /*timestamp*/,
+                             const int& /*i*/) {
+    double T[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) T[r * 4 + c] = rPose(r, c);
+    check(ctx_, plo_project(ctx_, T, 0, &last_proj_), "ProjSourcePtToSurface");
+    const int64_t cap = last_proj_.n_source > 0 ? last_proj_.n_source : 1;
+    sx_.resize(3 * cap); rx_.resize(3 * cap); rn_.resize(3 * cap); si_.resize(cap);
+    int64_t n = 0;
+    check(ctx_, plo_get_pairs(ctx_, sx_.data(), rx_.data(), rn_.data(), si_.data(), cap, &n), "plo_get_pairs");
+    si_.resize(n);
+    in_cloud->points.resize((size_t)n);
+    out_cloud->points.resize((size_t)n);
+    for (int64_t j = 0; j < n; ++j) {
+      PointT a, b;
+      std::memset(&a, 0, sizeof(PointT));
+      std::memset(&b, 0, sizeof(PointT));
+      float* af = reinterpret_cast<float*>(&a);
+      float* bf = reinterpret_cast<float*>(&b);
+      for (int k = 0; k < 3; ++k) { af[k] = sx_[3 * j + k]; bf[k] = rx_[3 * j + k]; bf[4 + k] = rn_[3 * j + k]; }
+      af[3] = bf[3] = 1.0f;
+      in_cloud->points[(size_t)j] = a;
+      out_cloud->points[(size_t)j] = b;
+    }
+  }
+
+  /* include/imls_icp.h:86-88, src/imls_icp.cpp:804-919 — the loop itself is the driver's
+   * (src/laser_odometry.cpp:524-647) and runs resident on the device. */
+  template <typename Mat4T>
+  bool Match(Mat4T& finalPose, Mat4T& covariance, const std::string& /*timestamp*/) {
+    double T[16];
+    check(ctx_, plo_register(ctx_, nullptr, T, &last_reg_), "Match");
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        finalPose(r, c) = T[r * 4 + c];
+        covariance(r, c) = (r == c) ? 1.0 : 0.0;   /* src/imls_icp.cpp:811 */
+      }
+    return last_reg_.status == PLO_REG_CONVERGED || last_reg_.status == PLO_REG_MAX_ITERS;
+  }
+
+  const std::vector<int32_t>& srcIndices() const { return si_; }
+  const plo_proj_stats& lastProjection() const { return last_proj_; }
+  const plo_reg_stats& lastRegistration() const { return last_reg_; }
+  plo_ctx* context() { return ctx_; }
+
+ private:
+  plo_ctx* ctx_;
+  plo_params params_;
+  plo_proj_stats last_proj_{};
+  plo_reg_stats last_reg_{};
+  std::vector<float> sx_, rx_, rn_;
+  std::vector<int32_t> si_;
+};
+
+/* include/solver.h:92-98 / src/solver.cpp:168-220 with the same argument list:
+ * (source_cloud, ref_cloud, ref_normals, deltaTrans, weights, timestamp).  `weights` may be
+ * empty (unit weights).  Always returns true, like the reference (:219). */
+template <typename Vec3T, typename Mat4T, typename WeightsT>
+bool SolveMotionEstimationProblemWeightedLS_CUDA(plo_ctx* ctx, const std::vector<Vec3T>& source_cloud,
+                                                 const std::vector<Vec3T>& ref_cloud, const std::vector<Vec3T>& ref_normals,
+                                                 Mat4T& deltaTrans, const WeightsT& weights, const std::string& /*timestamp*/) {
+  const size_t n = source_cloud.size();
+  std::vector<double> s(3 * n), d(3 * n), nn(3 * n), w;
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      s[3 * i + k] = source_cloud[i][k];
+      d[3 * i + k] = ref_cloud[i][k];
+      nn[3 * i + k] = ref_normals[i][k];
+    }
+  if ((size_t)weights.size() == n && n > 0) {
+    w.resize(n);
+    for (size_t i = 0; i < n; ++i) w[i] = weights[i];
+  }
+  double D[16];
+  check(ctx, plo_solve_wls_host(ctx, s.data(), d.data(), nn.data(), w.empty() ? nullptr : w.data(), (int64_t)n, D, nullptr),
+        "SolveMotionEstimationProblemWeightedLS_CUDA");
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) deltaTrans(r, c) = D[r * 4 + c];
+  return true;
+}
+
+}  // namespace plo
+
+#endif /* PLO_IMLS_ICP_CUDA_H */

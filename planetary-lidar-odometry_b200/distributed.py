@@ -35,7 +35,10 @@ def gather_results(local_rows: np.ndarray, local_units: list[int], n_units: int,
     if world == 1:
         table[local_units] = local_rows
         return table
-    per = (n_units + world - 1) // world
+    # shards may be ragged (sequences of different lengths): size the slots by the largest one
+    cnt = torch.tensor([len(local_units)], dtype=torch.int64, device=device)
+    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+    per = max(int(cnt.item()), 1)
     buf = torch.zeros((per, RESULT_WIDTH + 1), dtype=torch.float64, device=device)
     if len(local_units):
         buf[:len(local_units), :RESULT_WIDTH] = torch.as_tensor(np.asarray(local_rows), dtype=torch.float64, device=device)

@@ -424,3 +424,28 @@ def test_full_size_north_star_properties(oracle_mod):
     To, so = orc.register()
     assert sg["iters"] == so["iters"]
     assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+
+
+def test_cpp_host_driver_matches_python_driver(tmp_path):
+    """The C++ adapter (include/plo/imls_icp_cuda.h) + driver loop restated in C++
+    (host/odometry_driver.cpp, the shape of src/laser_odometry.cpp:416-683) gives the poses of
+    the Python mirror, in both the resident and the reference-style stepped mode."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "planetary-lidar-odometry_b200", "host", "odometry_driver")
+    assert os.path.exists(exe), "build the host driver (python -c 'import __graft_entry__ as g; g.build()')"
+    seq = W.Sequence(seed=2002, n_frames=3, max_points=10000)
+    frames = [seq.frame(k) for k in range(3)]
+    files = []
+    for k, f in enumerate(frames):
+        fn = str(tmp_path / f"frame{k}.bin")
+        f.astype(np.float32).tofile(fn)
+        files.append(fn)
+    P = plo.LaserOdometry(resident=True).run(frames)
+    for mode in ("resident", "stepped"):
+        out = str(tmp_path / f"poses_{mode}.txt")
+        subprocess.check_call([exe, "-", mode, out] + files)
+        got = np.loadtxt(out)
+        assert got.shape == (3, 8)
+        assert np.abs(got[:, 1:4] - P[:, :3, 3]).max() < 2e-6      # 6 decimals in the TUM file
