@@ -3,8 +3,8 @@
 // (setSourcePointCloud, src/imls_icp.cpp:74-78), including the non-finite strip of
 // RemoveNANandINFData (src/imls_icp.cpp:58-72).
 //
-// Index = "curve-sorted wide BVH": 48-bit Hilbert key per point (16 bit/axis over the
-// cloud's bounding cube) -> LSD radix sort (6 x 8 bit, stable) -> leaves of 32
+// Index = "curve-sorted wide BVH": 39-bit Hilbert key per point (over the
+// cloud's bounding cube, 13 bit/axis) -> LSD radix sort (4 x 10 bit, stable) -> leaves of 32
 // consecutive points -> levels of 32 consecutive nodes, one AABB per node.  Everything
 // is sized by the number of uploaded points, so no host synchronisation is needed:
 // non-finite points get the maximal key and +inf coordinates and sink to the tail.
@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdint>
 
 #include "plo_internal.cuh"
 #include "plo_scan.cuh"
@@ -22,9 +23,11 @@ namespace {
 
 constexpr int kSortTile = 4096;   // keys per block in the radix-sort kernels (256 thr x 16)
 constexpr int kSortItems = 16;
-constexpr int kRadixBits = 8;
+constexpr int kRadixBits = 10;    // 4 passes over the 39-bit key
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kKeyBits = 48;
+constexpr int kAxisBits = 13;     // Hilbert cells per axis = 2^13 (3.7 cm on a 300 m cube; ties keep input order)
+constexpr int kKeyBits = 40;
+constexpr int kPasses = kKeyBits / kRadixBits;
 
 __device__ __forceinline__ unsigned f2ord(float f) {
   unsigned u = __float_as_uint(f);
@@ -46,7 +49,7 @@ __global__ void k_init_bbox(unsigned* bbox) {
 
 // records -> float4 point (w = 1 if xyz finite) + float4 normal; finite count per block;
 // bounding box of the finite points.
-__global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ rec, int stride, int n,
+__global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ rec, int stride, int n, int vec16,
                                                       float4* __restrict__ praw, float4* __restrict__ nraw,
                                                       int* __restrict__ blockcnt, unsigned* __restrict__ bbox) {
   __shared__ int s_cnt[8];
@@ -58,9 +61,15 @@ __global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ r
   for (int j = 0; j < kTile / 256; ++j) {
     const int i = base + j * 256 + threadIdx.x;
     if (i < n) {
-      const float* r = reinterpret_cast<const float*>(rec + (size_t)i * stride);
-      const float x = r[0], y = r[1], z = r[2];
-      const float nx = r[4], ny = r[5], nz = r[6];
+      float x, y, z, nx, ny, nz;
+      if (vec16) {   // 16-byte aligned records: two 128-bit loads per point
+        const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)i * stride);
+        const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)i * stride + 16);
+        x = a.x; y = a.y; z = a.z; nx = b.x; ny = b.y; nz = b.z;
+      } else {
+        const float* r = reinterpret_cast<const float*>(rec + (size_t)i * stride);
+        x = r[0]; y = r[1]; z = r[2]; nx = r[4]; ny = r[5]; nz = r[6];
+      }
       const bool fin = finite3(x, y, z);
       praw[i] = make_float4(x, y, z, fin ? 1.f : 0.f);
       nraw[i] = make_float4(nx, ny, nz, 0.f);
@@ -108,13 +117,13 @@ __device__ __forceinline__ unsigned long long spread16(unsigned v) {
   return x;
 }
 
-// 48-bit Hilbert index of a 16-bit/axis cell (Skilling's transpose algorithm).  Unlike the Z-order
+// Hilbert index of a kAxisBits-per-axis cell (Skilling's transpose algorithm).  Unlike the Z-order
 // curve the Hilbert curve has no jumps: 32 (or 1024) consecutive points always form one compact blob,
 // so leaf and node boxes overlap far less (measured: -27 % leaves, -34 % level-1 nodes per query).
-__device__ __forceinline__ unsigned long long hilbert48(unsigned x0, unsigned x1, unsigned x2) {
+__device__ __forceinline__ unsigned long long hilbert_key(unsigned x0, unsigned x1, unsigned x2) {
   unsigned X[3] = {x0, x1, x2};
 #pragma unroll
-  for (unsigned Q = 1u << 15; Q > 1u; Q >>= 1) {
+  for (unsigned Q = 1u << (kAxisBits - 1); Q > 1u; Q >>= 1) {
     const unsigned P = Q - 1u;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -126,7 +135,7 @@ __device__ __forceinline__ unsigned long long hilbert48(unsigned x0, unsigned x1
   X[2] ^= X[1];
   unsigned t = 0u;
 #pragma unroll
-  for (unsigned Q = 1u << 15; Q > 1u; Q >>= 1)
+  for (unsigned Q = 1u << (kAxisBits - 1); Q > 1u; Q >>= 1)
     if (X[2] & Q) t ^= Q - 1u;
   X[0] ^= t; X[1] ^= t; X[2] ^= t;
   return (spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2]);
@@ -149,7 +158,8 @@ __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ praw, i
   tile_ranks(fin, rank);
   const float lox = ord2f(bbox[0]), loy = ord2f(bbox[1]), loz = ord2f(bbox[2]);
   const float ext = fmaxf(fmaxf(ord2f(bbox[3]) - lox, ord2f(bbox[4]) - loy), ord2f(bbox[5]) - loz);
-  const float scale = (ext > 0.f && isfinite(ext)) ? 65535.f / ext : 0.f;
+  constexpr unsigned kCellMax = (1u << kAxisBits) - 1u;
+  const float scale = (ext > 0.f && isfinite(ext)) ? (float)kCellMax / ext : 0.f;
   const int off = blockoff[blockIdx.x];
 #pragma unroll
   for (int j = 0; j < kTile / 256; ++j) {
@@ -159,10 +169,10 @@ __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ praw, i
     int ci = -1;
     if (fin[j]) {
       ci = off + rank[j];
-      const unsigned qx = min(65535u, (unsigned)fmaxf(0.f, (p[j].x - lox) * scale));
-      const unsigned qy = min(65535u, (unsigned)fmaxf(0.f, (p[j].y - loy) * scale));
-      const unsigned qz = min(65535u, (unsigned)fmaxf(0.f, (p[j].z - loz) * scale));
-      key = hilbert48(qx, qy, qz);
+      const unsigned qx = min(kCellMax, (unsigned)fmaxf(0.f, (p[j].x - lox) * scale));
+      const unsigned qy = min(kCellMax, (unsigned)fmaxf(0.f, (p[j].y - loy) * scale));
+      const unsigned qz = min(kCellMax, (unsigned)fmaxf(0.f, (p[j].z - loz) * scale));
+      key = hilbert_key(qx, qy, qz);
     }
     cidx[i] = ci;
     keys[i] = key;
@@ -199,9 +209,9 @@ __global__ void __launch_bounds__(256) k_compact_source(const float4* __restrict
 // ---- LSD radix sort, one 8-bit digit per pass -------------------------------------
 
 __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __restrict__ keys, int n, int shift,
-                                                   int nb, int* __restrict__ hist) {
+                                                   int nb, int* __restrict__ hist, int* __restrict__ digit_total) {
   __shared__ int s_h[kRadix];
-  s_h[threadIdx.x] = 0;
+  for (int d = threadIdx.x; d < kRadix; d += 256) s_h[d] = 0;
   __syncthreads();
   const int base = blockIdx.x * kSortTile;
 #pragma unroll
@@ -210,7 +220,55 @@ __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __r
     if (i < n) atomicAdd(&s_h[(unsigned)(keys[i] >> shift) & (kRadix - 1)], 1);
   }
   __syncthreads();
-  hist[threadIdx.x * nb + blockIdx.x] = s_h[threadIdx.x];
+  for (int d = threadIdx.x; d < kRadix; d += 256) {
+    const int v = s_h[d];
+    hist[d * nb + blockIdx.x] = v;
+    if (v) atomicAdd(&digit_total[d], v);
+  }
+}
+
+// one block per digit: base = sum of the totals of all smaller digits, then an exclusive scan of the
+// digit's row (one entry per sort block) — replaces a single-block scan of the whole table
+__global__ void __launch_bounds__(256) k_sort_scan(int* __restrict__ hist, int nb, const int* __restrict__ digit_total) {
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int d = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int part = 0;
+  for (int j = threadIdx.x; j < d; j += 256) part += digit_total[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(PLO_FULL_MASK, part, o);
+  if (lane == 0) s_warp[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_warp[w];
+    s_carry = t;
+  }
+  __syncthreads();
+  int* row = hist + (size_t)d * nb;
+  for (int base = 0; base < nb; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nb) ? row[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(PLO_FULL_MASK, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();   // s_warp reuse
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) woff += (w < warp) ? s_warp[w] : 0;
+    const int carry = s_carry;
+    if (i < nb) row[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + woff + inc;
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned long long* __restrict__ keys_in,
@@ -222,7 +280,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned long long* 
   __shared__ int s_g[kRadix];      // global base of (digit, this block)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < 8 * kRadix; q += 256) (&s_w[0][0])[q] = 0;
-  s_g[threadIdx.x] = hist_scanned[threadIdx.x * nb + blockIdx.x];
+  for (int d = threadIdx.x; d < kRadix; d += 256) s_g[d] = hist_scanned[d * nb + blockIdx.x];
   __syncthreads();
   const int base = blockIdx.x * kSortTile + warp * (kSortItems * 32);
   unsigned long long key[kSortItems];
@@ -244,10 +302,10 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned long long* 
     rank[j] = pre + __popc(peers & ((1u << lane) - 1u));
   }
   __syncthreads();
-  {
+  for (int d = threadIdx.x; d < kRadix; d += 256) {
     int run = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { int t = s_w[w][threadIdx.x]; s_w[w][threadIdx.x] = run; run += t; }
+    for (int w = 0; w < 8; ++w) { int t = s_w[w][d]; s_w[w][d] = run; run += t; }
   }
   __syncthreads();
 #pragma unroll
@@ -392,10 +450,11 @@ int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stri
     PLO_CUDA(c, c->lvl_hi[l].reserve(sizeof(float4) * pad[l]));
   }
   cudaStream_t s = c->stream;
+  const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
   if (c->ev[0]) cudaEventRecord(c->ev[0], s);
   k_init_bbox<<<1, 32, 0, s>>>(c->bbox.as<unsigned>());
   LAUNCH_CHECK(c);
-  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, c->t_praw.as<float4>(),
+  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, vec16, c->t_praw.as<float4>(),
                                     c->t_nraw.as<float4>(), c->blockcnt.as<int>(), c->bbox.as<unsigned>());
   LAUNCH_CHECK(c);
   k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_target);
@@ -404,10 +463,14 @@ int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stri
                             c->t_cidx.as<int>(), c->keys[0].as<unsigned long long>(), c->vals[0].as<int>());
   LAUNCH_CHECK(c);
   int cur = 0;
-  for (int shift = 0; shift < kKeyBits; shift += kRadixBits) {
-    k_sort_hist<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), (int)n, shift, nbs, c->hist.as<int>());
+  PLO_CUDA(c, c->digit_total.reserve(sizeof(int) * kPasses * kRadix));
+  PLO_CUDA(c, cudaMemsetAsync(c->digit_total.p, 0, sizeof(int) * kPasses * kRadix, s));
+  for (int pass = 0; pass < kPasses; ++pass) {
+    const int shift = pass * kRadixBits;
+    int* tot = c->digit_total.as<int>() + pass * kRadix;
+    k_sort_hist<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), (int)n, shift, nbs, c->hist.as<int>(), tot);
     LAUNCH_CHECK(c);
-    k_scan_exclusive<<<1, 1024, 0, s>>>(c->hist.as<int>(), kRadix * nbs, nullptr);
+    k_sort_scan<<<kRadix, 256, 0, s>>>(c->hist.as<int>(), nbs, tot);
     LAUNCH_CHECK(c);
     k_sort_scatter<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), c->vals[cur].as<int>(),
                                        c->keys[cur ^ 1].as<unsigned long long>(), c->vals[cur ^ 1].as<int>(), (int)n,
@@ -456,7 +519,8 @@ int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t st
   PLO_CUDA(c, c->s_n.reserve(sizeof(float4) * n));
   PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * (size_t)(nb + 1)));
   cudaStream_t s = c->stream;
-  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, c->s_praw.as<float4>(),
+  const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
+  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, vec16, c->s_praw.as<float4>(),
                                     c->s_nraw.as<float4>(), c->blockcnt.as<int>(), nullptr);
   LAUNCH_CHECK(c);
   k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_source);

@@ -154,7 +154,7 @@ void plo_destroy(plo_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
-                    &c->vals[0], &c->vals[1], &c->hist, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
+                    &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
                     &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->chunk_counter, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};

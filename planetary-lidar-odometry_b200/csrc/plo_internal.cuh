@@ -101,7 +101,7 @@ struct plo_ctx {
   int n_levels = 0;
   int64_t level_nodes[PLO_MAX_LEVELS] = {0};
   DevBuf t_stage, t_praw, t_nraw, t_cidx, blockcnt, bbox;
-  DevBuf keys[2], vals[2], hist;
+  DevBuf keys[2], vals[2], hist, digit_total;
   DevBuf pts_sorted, nrm_sorted, nrm_pca, pos_of_cidx;
   DevBuf lvl_lo[PLO_MAX_LEVELS], lvl_hi[PLO_MAX_LEVELS];
 
