@@ -90,6 +90,17 @@ __device__ __forceinline__ float hi_from_lo(float lo) { return __fmul_ru(lo, 1.0
 // D (double) -> float threshold for lower-bound tests, with a safety margin
 __device__ __forceinline__ float bound_f(double D) { return __fmul_ru(__double2float_ru(D), 1.000001f); }
 
+// triangle-inequality bound, everything rounded up: the k points nearest to x_ref (k-th squared distance
+// <= kref) are all within sqrt(kref) + |x - x_ref| of x; returns the float threshold for lower-bound tests
+__device__ __forceinline__ float tri_bound(float kref, float x, float y, float z, float rx, float ry, float rz) {
+  const float ax = fmaxf(fabsf(__fsub_ru(x, rx)), fabsf(__fsub_rd(x, rx)));
+  const float ay = fmaxf(fabsf(__fsub_ru(y, ry)), fabsf(__fsub_rd(y, ry)));
+  const float az = fmaxf(fabsf(__fsub_ru(z, rz)), fabsf(__fsub_rd(z, rz)));
+  const float s2 = __fadd_ru(__fadd_ru(__fmul_ru(ax, ax), __fmul_ru(ay, ay)), __fmul_ru(az, az));
+  const float rad = __fadd_ru(__fsqrt_ru(kref), __fsqrt_ru(s2));
+  return __fmul_ru(__fmul_ru(rad, rad), 1.000002f);
+}
+
 __device__ __forceinline__ double dist2_exact(double qx, double qy, double qz, const float4 p) {
   const double dx = __dsub_rn(qx, (double)p.x), dy = __dsub_rn(qy, (double)p.y), dz = __dsub_rn(qz, (double)p.z);
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -313,7 +324,9 @@ __device__ __forceinline__ void collect_leaf(const MapView& m, int leaf, float q
   col.appended += __popc(b);
 }
 
-template <int LEVEL>
+// ORDERED: visit the children nearest-centre-first (any order is exact).  Worth its cost only when
+// the bound is loose (no reference): the densest neighbourhood of q then tightens it early.
+template <int LEVEL, bool ORDERED>
 struct Collect {
   static __device__ __forceinline__ void run(const MapView& m, int node, float qx, float qy, float qz, float r2f_lo, double r2,
                                              bool allow_self, int k, WarpScratch& ws, Collector& col, SearchStats& st,
@@ -322,22 +335,24 @@ struct Collect {
     st.n_node++;
     const float4 lo = __ldg(&m.lo[LEVEL - 1][child]), hi = __ldg(&m.hi[LEVEL - 1][child]);
     const float bd = box_lo2(qx, qy, qz, lo, hi);
-    // visiting order (any order is exact): nearest box centre first, so that a loose bound is
-    // tightened by the densest neighbourhood of q as early as possible
-    const float cx = qx - 0.5f * (lo.x + hi.x), cy = qy - 0.5f * (lo.y + hi.y), cz = qz - 0.5f * (lo.z + hi.z);
-    const unsigned key = __float_as_uint(fminf(cx * cx + cy * cy + cz * cz, 3.0e38f));
+    unsigned key = 0u;
+    if constexpr (ORDERED) {
+      const float cx = qx - 0.5f * (lo.x + hi.x), cy = qy - 0.5f * (lo.y + hi.y), cz = qz - 0.5f * (lo.z + hi.z);
+      key = __float_as_uint(fminf(cx * cx + cy * cy + cz * cz, 3.0e38f));
+    }
     unsigned mask = __ballot_sync(PLO_FULL_MASK, bd <= col.Df);
     int shrinks_seen = col.shrinks;
     while (mask != 0u) {
-      int c;
-      if ((mask & (mask - 1)) == 0u) c = __ffs(mask) - 1;   // single child left
-      else {
-        const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) ? key : 0xffffffffu);
-        c = __ffs(__ballot_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) && key == mn)) - 1;
+      int c = __ffs(mask) - 1;
+      if constexpr (ORDERED) {
+        if ((mask & (mask - 1)) != 0u) {   // more than one child left
+          const unsigned mn = __reduce_min_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) ? key : 0xffffffffu);
+          c = __ffs(__ballot_sync(PLO_FULL_MASK, ((mask >> lane) & 1u) && key == mn)) - 1;
+        }
       }
       mask &= ~(1u << c);
       if constexpr (LEVEL == 1) collect_leaf(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
-      else Collect<LEVEL - 1>::run(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+      else Collect<LEVEL - 1, ORDERED>::run(m, node * PLO_FANOUT + c, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
       if (col.shrinks != shrinks_seen) {   // the bound shrank below: re-test the remaining children
         shrinks_seen = col.shrinks;
         mask &= __ballot_sync(PLO_FULL_MASK, bd <= col.Df);
@@ -347,10 +362,11 @@ struct Collect {
 };
 
 // exact k-NN of q (float32 coordinates, as the reference stores the transformed point).
-// D0: a proven upper bound of the k-th distance (squared) or +inf; with `refine` the greedy
-// bound is evaluated as well.  Result: lane j holds neighbour j (d2 = +inf where not filled).
+// Df0: float threshold derived from a proven upper bound of the k-th distance (squared), or +inf;
+// with `refine` the greedy bound is evaluated as well and the walk is ordered.
+// Result: lane j holds neighbour j (d2 = +inf where not filled).
 template <int LEVELS>
-__device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, float qz, double D0, bool refine, double r2,
+__device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, float qz, float Df0, bool refine, double r2,
                                          int k, bool allow_self, WarpScratch& ws, TopK& tk, SearchStats& st, int lane) {
   st.n_leaf = st.n_node = st.n_cand = 0;
   tk.d2 = CUDART_INF;
@@ -359,16 +375,18 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
   if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) return;
   const float r2f_lo = __double2float_rd(r2);   // "certainly within the radius" threshold
   Collector col;
-  col.Df = bound_f(fmin(D0, r2));
-  if (refine || !(D0 < r2)) {
-    const unsigned best = Greedy<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, allow_self, st, lane);
-    const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
-    if (kth < 0x7f800000u) col.Df = fminf(col.Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
-  }
+  col.Df = fminf(Df0, bound_f(r2));
   col.count = 0;
   col.appended = 0;
   col.shrinks = 0;
-  Collect<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+  if (refine) {
+    const unsigned best = Greedy<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, allow_self, st, lane);
+    const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
+    if (kth < 0x7f800000u) col.Df = fminf(col.Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
+    Collect<LEVELS, true>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+  } else {
+    Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+  }
   __syncwarp();
   st.n_cand = col.appended + 100000 * col.shrinks;
   exact_distances(m, ws, col.count, qx, qy, qz, r2, allow_self, lane);
@@ -384,7 +402,7 @@ template <int LEVELS>
 __device__ __noinline__ void knn1_noself(const MapView& m, float qx, float qy, float qz, double r2, WarpScratch* ws) {
   TopK tk;
   SearchStats st;
-  knn_topk<LEVELS>(m, qx, qy, qz, CUDART_INF, true, r2, 1, false, *ws, tk, st, threadIdx.x & 31);
+  knn_topk<LEVELS>(m, qx, qy, qz, CUDART_INF_F, true, r2, 1, false, *ws, tk, st, threadIdx.x & 31);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -406,7 +424,11 @@ __device__ __forceinline__ bool angle_exceeds(double ax, double ay, double az, d
   const float prod = (float)(na2 * nb2);
   if (prod > 1e-30f && prod < 1e30f) {
     const float ce = (float)dot * rsqrtf(prod);
-    if (fabsf(ce) < 0.999f && fabsf(ce - (float)P.cos_thr) > 1e-5f) return ce < (float)P.cos_thr;
+    const float ct = (float)P.cos_thr;
+    // clearly inside the cone: angle <= thr, or cos > 1 by rounding (acos = NaN, compares false): keep
+    if (ce > ct + 1e-5f) return false;
+    // clearly outside (and not at cos < -1, where the reference's acos is NaN and the point is kept)
+    if (ce < ct - 1e-5f && ce > -0.999f) return true;
   }
   const double c = dot / (sqrt(na2) * sqrt(nb2));
   if (!(c == c)) return false;
@@ -419,7 +441,7 @@ struct ProjectOut {
   float4* qy;        // projected point y (float32)
   float4* qn;        // normal of the 1-NN (float32)
   int* status;
-  double* kd2;       // k-th neighbour distance of this projection (+inf if the list is not full)
+  float* kd2f;       // k-th neighbour distance (squared, rounded up) of this projection; +inf if the list is not full
   // hooks
   double* height;
   int* nn1_idx;
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
    if (lane == 0) c0 = atomicAdd(chunk_counter, 1) * chunk;
    c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
    if (c0 >= n_src) break;
-   double carry_kd2 = CUDART_INF, carry_x = 0.0, carry_y = 0.0, carry_z = 0.0;
+   float carry_kf = CUDART_INF_F, carry_x = 0.f, carry_y = 0.f, carry_z = 0.f;
    const int c1 = min(c0 + chunk, n_src);
    for (int qi = c0; qi < c1; ++qi) {
     const float4 p = __ldg(&sp[qi]);
@@ -479,35 +501,33 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
     // bounds of the k-th distance by the triangle inequality: the k points that were nearest to a
     // reference position x_ref are all within sqrt(kd2_ref) + |x - x_ref| of x.  Reference =
     // this query in the previous projection (temporal) and the previous query of the chunk (carry).
-    double D0 = CUDART_INF, ref_kd2 = CUDART_INF;
+    // All in float with upward rounding (conservative); kd2 references are stored rounded up.
+    float Df0 = CUDART_INF_F, ref_kf = CUDART_INF_F;
     if (use_prev) {
-      const double kprev = out.kd2[qi];
-      if (kprev < CUDART_INF) {
+      const float kprev = out.kd2f[qi];
+      if (kprev < CUDART_INF_F) {
         const float4 xp = out.qx[qi];
-        const double ex = qx - (double)xp.x, ey = qy - (double)xp.y, ez = qz - (double)xp.z;
-        const double rad = sqrt(kprev) + sqrt(ex * ex + ey * ey + ez * ez);
-        D0 = rad * rad * (1.0 + 1e-9);
-        ref_kd2 = kprev;
+        Df0 = tri_bound(kprev, xf, yf, zf, xp.x, xp.y, xp.z);
+        ref_kf = kprev;
       }
     }
-    if (carry_kd2 < CUDART_INF) {
-      const double ex = qx - carry_x, ey = qy - carry_y, ez = qz - carry_z;
-      const double rad = sqrt(carry_kd2) + sqrt(ex * ex + ey * ey + ez * ez);
-      const double Dc = rad * rad * (1.0 + 1e-9);
-      if (Dc < D0) { D0 = Dc; ref_kd2 = carry_kd2; }
+    if (carry_kf < CUDART_INF_F) {
+      const float Dc = tri_bound(carry_kf, xf, yf, zf, carry_x, carry_y, carry_z);
+      if (Dc < Df0) { Df0 = Dc; ref_kf = carry_kf; }
     }
-    if (!(D0 == D0)) D0 = CUDART_INF;
+    if (!(Df0 == Df0)) Df0 = CUDART_INF_F;
     // a bound more than 2.5x (in distance) above its reference would buffer > 6x k candidates:
-    // evaluate the greedy bound as well
-    const bool refine = !(D0 <= 6.25 * ref_kd2);
+    // evaluate the greedy bound as well (and walk nearest-first)
+    const bool refine = !(Df0 < CUDART_INF_F) || !(Df0 <= 6.25f * ref_kf);
 
     TopK tk;
     SearchStats ss;
-    if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, D0, refine, P.r2, P.k, true, ws, tk, ss, lane);   // :372-375 ALLOW_SELF_MATCH
+    if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane);   // :372-375 ALLOW_SELF_MATCH
     else { tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1; ss.n_leaf = ss.n_node = ss.n_cand = 0; }
     const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
     const double kd2_now = __shfl_sync(PLO_FULL_MASK, tk.d2, P.k - 1);
-    carry_kd2 = kd2_now; carry_x = qx; carry_y = qy; carry_z = qz;
+    const float kd2f_now = (kd2_now < CUDART_INF) ? __double2float_ru(kd2_now) : CUDART_INF_F;
+    carry_kf = kd2f_now; carry_x = xf; carry_y = yf; carry_z = zf;
 
     // ---- 1-NN without self match (:601-609) ----
     int i1 = -1, pos1 = -1;
@@ -579,7 +599,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
       }
       out.qx[qi] = ox; out.qy[qi] = oy; out.qn[qi] = on;
       out.status[qi] = status;
-      out.kd2[qi] = kd2_now;
+      out.kd2f[qi] = kd2f_now;
     }
     if (hooks) {
       if (lane < P.k) {
@@ -645,7 +665,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_pca_normals(const __gri
     if (isfinite(p.x)) {
       TopK tk;
       SearchStats ss;
-      knn_topk<LEVELS>(m, p.x, p.y, p.z, CUDART_INF, true, P.r_normal2, P.k_normal, false, ws, tk, ss, lane);
+      knn_topk<LEVELS>(m, p.x, p.y, p.z, CUDART_INF_F, true, P.r_normal2, P.k_normal, false, ws, tk, ss, lane);
       const bool has = (lane < P.k_normal) && (tk.d2 < CUDART_INF);
       const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, has));
       if (cnt == P.k_normal) {
@@ -740,7 +760,7 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   ProjectOut out;
   out.qx = c->q_x.as<float4>(); out.qy = c->q_y.as<float4>(); out.qn = c->q_n.as<float4>();
   out.status = c->q_status.as<int>();
-  out.kd2 = c->q_kd2.as<double>();
+  out.kd2f = c->q_kd2.as<float>();
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
   out.search_stats = c->q_stats.as<int>();
