@@ -457,12 +457,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
                                                                           const float4* __restrict__ sn,
                                                                           const DevCounts* __restrict__ counts,
                                                                           const DevState* __restrict__ st, DevParams P,
-                                                                          ProjectOut out, int hooks, int use_prev, int chunk,
+                                                                          ProjectOut out, int hooks, int chunk,
                                                                           int* __restrict__ chunk_counter) {
   if (st->done) return;
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const int use_prev = st->use_prev;
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
   // rPose rows (src/laser_odometry.cpp:530-535)
@@ -741,16 +742,15 @@ void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int ho
   const DevCounts* dc = c->counts.as<DevCounts>();
   const DevState* st = c->state.as<DevState>();
   int* cc = c->chunk_counter.as<int>();
-  const int up = c->prev_valid ? 1 : 0;
   const int T = kWarpsPerBlock * 32;
   switch (c->n_levels) {   // an empty map (n_levels == 0) never walks the tree: any instantiation does
     case 0:
-    case 1: k_project<PCA, 1><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
-    case 2: k_project<PCA, 2><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
-    case 3: k_project<PCA, 3><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
-    case 4: k_project<PCA, 4><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
-    case 5: k_project<PCA, 5><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
-    default: k_project<PCA, 6><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, up, chunk, cc); break;
+    case 1: k_project<PCA, 1><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    case 2: k_project<PCA, 2><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    case 3: k_project<PCA, 3><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    case 4: k_project<PCA, 4><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    case 5: k_project<PCA, 5><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    default: k_project<PCA, 6><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
   }
 }
 }  // namespace

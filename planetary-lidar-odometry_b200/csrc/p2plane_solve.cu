@@ -214,14 +214,23 @@ __device__ int solve_ldlt6(const double H21[21], const double g[6], double count
   return rank;
 }
 
-__global__ void __launch_bounds__(64) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
-                                                     DevParams P, int advance_loop) {
-  if (advance_loop && st->done) return;
+__global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
+                                                       DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond) {
+  if (advance_loop && st->done) {
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
+    return;
+  }
   __shared__ double s_sum[PLO_NSUM];
-  if (threadIdx.x < PLO_NSUM) {
-    double v = 0.0;
-    for (int b = 0; b < n_partials; ++b) v += partials[(size_t)b * PLO_NSUM + threadIdx.x];   // fixed order
-    s_sum[threadIdx.x] = v;
+  {
+    // value t is summed by warp (t mod 32): lane-strided partial sums in a fixed order, fixed shuffle tree
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = warp; t < PLO_NSUM; t += 32) {
+      double v = 0.0;
+      for (int b = lane; b < n_partials; b += 32) v += partials[(size_t)b * PLO_NSUM + t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PLO_FULL_MASK, v, o);
+      if (lane == 0) s_sum[t] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -237,6 +246,7 @@ __global__ void __launch_bounds__(64) k_solve_update(const double* __restrict__ 
   if (advance_loop && count < (double)P.correspond_number) {   // src/laser_odometry.cpp:570-576
     st->status = PLO_REG_TOO_FEW_PAIRS;
     st->done = 1;
+    if (use_cond) cudaGraphSetConditional(cond, 0);
     return;
   }
   double H[21], g[6];
@@ -268,11 +278,13 @@ __global__ void __launch_bounds__(64) k_solve_update(const double* __restrict__ 
     }
   for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
   st->iters += 1;
+  st->use_prev = 1;   // the projection just consumed left its k-th distances behind
   if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
   else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
+  if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
 }
 
-__global__ void k_init_state(DevState* st, const double* T0) {
+__global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 16; ++i) {
       const double id = (i % 5 == 0) ? 1.0 : 0.0;
@@ -287,6 +299,8 @@ __global__ void k_init_state(DevState* st, const double* T0) {
     st->status = 0;
     st->rank = 0;
     st->done = 0;
+    st->use_prev = use_prev;
+    st->pad = 0;
   }
 }
 
@@ -358,13 +372,13 @@ int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null) {
     PLO_CUDA(c, cudaMemcpyAsync(c->scratch.p, T0_host_or_null, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
     dT0 = c->scratch.as<double>();
   }
-  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0);
+  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0, c->prev_valid ? 1 : 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
 }
 
-int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop) {
+int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long cond_handle) {
   const int g = reduce_grid(c, c->m_raw);
   PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
   if (c->m_raw > 0) {
@@ -374,8 +388,8 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop) {
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
   }
-  k_solve_update<<<1, 64, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), c->dprm,
-                                          advance_loop ? 1 : 0);
+  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), c->dprm,
+                                            advance_loop ? 1 : 0, (cudaGraphConditionalHandle)cond_handle, cond_handle ? 1 : 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
@@ -392,7 +406,8 @@ int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const do
   }
   DevParams P = c->dprm;
   P.weight_mode = PLO_W_UNIT;   // caller-supplied weights are used as they are
-  k_solve_update<<<1, 64, 0, c->stream>>>(c->partials.as<double>(), n > 0 ? g : 0, c->state.as<DevState>(), P, 0);
+  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), n > 0 ? g : 0, c->state.as<DevState>(), P, 0,
+                                            (cudaGraphConditionalHandle)0, 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;

@@ -6,11 +6,16 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <new>
+#include <vector>
 
 #include "plo_internal.cuh"
 
 static std::string g_create_error;
+extern "C" {
+static void destroy_loop_graph(plo_ctx* c);
+}
 
 cudaError_t DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return cudaSuccess;
@@ -164,6 +169,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->h_counts) cudaFreeHost(c->h_counts);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->ev_proj) cudaEventDestroy(e);
+  destroy_loop_graph(c);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -175,6 +181,7 @@ int plo_set_stream(plo_ctx* c, void* cuda_stream) {
   PLO_CUDA(c, cudaSetDevice(c->device));
   PLO_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  destroy_loop_graph(c);
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
   return PLO_OK;
@@ -457,12 +464,93 @@ int plo_get_normal_equations(plo_ctx* c, double H21[21], double g6[6], double* s
   return PLO_OK;
 }
 
+// everything a captured iteration depends on; the loop graph is rebuilt when any of it changes
+static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
+  std::vector<unsigned long long> v;
+  auto add = [&v](const void* p) { v.push_back((unsigned long long)(uintptr_t)p); };
+  add(c->stream);
+  add(c->pts_sorted.p); add(c->nrm_sorted.p); add(c->nrm_pca.p);
+  for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
+  add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p);
+  add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
+  v.push_back((unsigned long long)c->n_levels);
+  v.push_back((unsigned long long)c->n_raw_t);   // MapView.n_raw is a kernel argument
+  v.push_back((unsigned long long)c->m_raw);     // launch geometry derives from it
+  const unsigned char* pb = reinterpret_cast<const unsigned char*>(&c->dprm);
+  for (size_t i = 0; i + 8 <= sizeof(DevParams); i += 8) { unsigned long long w; memcpy(&w, pb + i, 8); v.push_back(w); }
+  return v;
+}
+
+static void destroy_loop_graph(plo_ctx* c) {
+  if (c->loop_exec) cudaGraphExecDestroy(c->loop_exec);
+  if (c->loop_graph) cudaGraphDestroy(c->loop_graph);
+  c->loop_exec = nullptr;
+  c->loop_graph = nullptr;
+  c->loop_sig.clear();
+}
+
+// WHILE conditional node whose body is one ICP iteration (chunk-counter reset, k_project,
+// k_reduce_pairs, k_solve_update); k_solve_update sets the condition from the device-side state.
+static int build_loop_graph(plo_ctx* c) {
+  destroy_loop_graph(c);
+  cudaGraph_t g = nullptr;
+  if (cudaGraphCreate(&g, 0) != cudaSuccess) return -1;
+  cudaGraphConditionalHandle handle;
+  if (cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) { cudaGraphDestroy(g); return -1; }
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  if (cudaGraphAddNode(&node, g, nullptr, 0, &np) != cudaSuccess) { cudaGraphDestroy(g); return -1; }
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  if (cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGraphDestroy(g);
+    return -1;
+  }
+  const int64_t launches_before = c->launches;
+  int rc = plo_launch_project(c, false);
+  if (rc == PLO_OK) rc = plo_launch_reduce_solve(c, true, (unsigned long long)handle);
+  c->launches = launches_before;   // capture is not execution
+  cudaGraph_t captured = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &captured);
+  if (rc != PLO_OK || e != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return -1; }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return -1; }
+  c->loop_graph = g;
+  c->loop_exec = exec;
+  c->loop_sig = loop_signature(c);
+  return 0;
+}
+
 static int enqueue_register(plo_ctx* c, const double* T0) {
   PLO_TRY(plo_reserve_query_buffers(c, false));
+  PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
+  PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
   if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
   PLO_TRY(plo_launch_init_state(c, T0));
-  // every iteration is enqueued up front; kernels of iterations after convergence see the
-  // device-side `done` flag and return at once — no host round trip inside the loop
+  if (c->prm.iterations <= 0) { c->hooks_valid = false; return PLO_OK; }
+  // Product path: the loop is a CUDA graph with a device-evaluated WHILE condition — exactly the
+  // iterations that are needed run, with no host round trip.  With per-launch profiling (or if the
+  // driver refuses conditional nodes) every iteration is enqueued up front instead; kernels of
+  // iterations after convergence then see the device-side `done` flag and return at once.
+  if (!c->profiling && c->graph_ok && c->m_raw > 0) {
+    if (!c->loop_exec || c->loop_sig != loop_signature(c)) {
+      if (build_loop_graph(c) != 0) c->graph_ok = false;
+    }
+    if (c->loop_exec) {
+      const bool prev = c->prev_valid;
+      (void)prev;
+      PLO_CUDA(c, cudaGraphLaunch(c->loop_exec, c->stream));
+      c->prev_valid = true;
+      c->projected = true;
+      c->hooks_valid = false;
+      c->graph_launched = true;
+      return PLO_OK;
+    }
+  }
+  c->graph_launched = false;
   if (c->profiling) {
     while ((int)c->ev_proj.size() < 2 * c->prm.iterations) {
       cudaEvent_t e;
@@ -479,6 +567,14 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
   c->projected = true;
   c->hooks_valid = false;
   return PLO_OK;
+}
+
+// kernels a graph-launched loop executed (the host did not enqueue them one by one)
+static void count_graph_launches(plo_ctx* c, const DevState* s) {
+  if (!c->graph_launched) return;
+  const int bodies = s->iters + (s->status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0);
+  c->launches += 3 * (int64_t)bodies;
+  c->graph_launched = false;
 }
 
 static void fill_reg_stats(const DevState* s, plo_reg_stats* st, int iterations) {
@@ -502,6 +598,7 @@ int plo_register(plo_ctx* c, const double T0[16], double T[16], plo_reg_stats* s
   cudaEventRecord(c->ev[3], c->stream);
   c->ev_reg_pending = true;
   PLO_TRY(fetch_state(c));
+  count_graph_launches(c, c->h_state);
   memcpy(T, c->h_state->rPose, sizeof(double) * 16);
   if (stats) fill_reg_stats(c->h_state, stats, c->prm.iterations);
   if (c->profiling) {
@@ -550,12 +647,14 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   DevState* h_slots = nullptr;
   PLO_CUDA(c, cudaMallocHost(&h_slots, sizeof(DevState) * (size_t)count));
   int rc = PLO_OK;
+  int graph_units = 0;
   for (int i = 0; i < count && rc == PLO_OK; ++i) {
     // the staging buffers are reused pair after pair: stream order keeps that safe
     rc = on_device ? plo_set_target_device(c, targets[i], n_tgt[i], stride) : plo_set_target(c, targets[i], n_tgt[i], stride);
     if (rc == PLO_OK) rc = on_device ? plo_set_source_device(c, sources[i], n_src[i], stride) : plo_set_source(c, sources[i], n_src[i], stride);
     if (rc == PLO_OK) rc = enqueue_register(c, nullptr);
     if (rc == PLO_OK) {
+      if (c->graph_launched) { graph_units++; c->graph_launched = false; }
       k_store_result<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), slots.as<DevState>() + i);
       c->launches++;
       if (cudaGetLastError() != cudaSuccess) rc = plo_fail(c, PLO_ERR_CUDA, "plo_register_batch: k_store_result launch failed");
@@ -570,6 +669,7 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   }
   if (rc == PLO_OK) {
     for (int i = 0; i < count; ++i) {
+      if (graph_units > 0) c->launches += 3 * (int64_t)(h_slots[i].iters + (h_slots[i].status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0));
       memcpy(T_out + 16 * (size_t)i, h_slots[i].rPose, sizeof(double) * 16);
       if (stats_out) fill_reg_stats(&h_slots[i], &stats_out[i], c->prm.iterations);
     }
@@ -599,7 +699,8 @@ int plo_time_project_kernel(plo_ctx* c, const double T[16], int32_t reps, float*
   PLO_TRY(plo_reserve_query_buffers(c, false));
   if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
   PLO_TRY(plo_launch_init_state(c, T));
-  PLO_TRY(plo_launch_project(c, false));   // warm-up
+  PLO_TRY(plo_launch_project(c, false));   // warm-up; leaves the k-th distances for the temporal bound
+  PLO_TRY(plo_launch_init_state(c, T));
   cudaEvent_t a, b;
   PLO_CUDA(c, cudaEventCreate(&a));
   PLO_CUDA(c, cudaEventCreate(&b));

@@ -51,6 +51,8 @@ struct DevState {
   int status;     // 0 while running, else plo_reg_status
   int rank;
   int done;       // kernels of later iterations return immediately when set
+  int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds (temporal bound usable)
+  int pad;
 };
 
 struct DevCounts {
@@ -126,6 +128,12 @@ struct plo_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_index = 0.f, ms_register = 0.f;
   bool ev_index_pending = false, ev_reg_pending = false;
+  // resident loop as a CUDA graph: a WHILE conditional node whose body is one ICP iteration
+  cudaGraph_t loop_graph = nullptr;
+  cudaGraphExec_t loop_exec = nullptr;
+  std::vector<unsigned long long> loop_sig;
+  bool graph_launched = false;   // the last enqueue_register went through the graph
+  bool graph_ok = true;      // cleared if the driver rejects conditional nodes: falls back to enqueue-all
   bool profiling = false;
   std::vector<cudaEvent_t> ev_proj;   // 2 per loop iteration when profiling
   float ms_project_mean = 0.f;
@@ -158,7 +166,7 @@ int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);
 int plo_reserve_query_buffers(plo_ctx* c, bool hooks);
 // ---- p2plane_solve.cu -------------------------------------------------------------
-int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop);
+int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long cond_handle = 0ull);
 int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const double* d_ref,
                                        const double* d_nrm, const double* d_w, int64_t n);
 int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null);
