@@ -44,7 +44,10 @@ namespace {
 
 constexpr int kCap = 128;          // candidate buffer entries per warp
 constexpr int kWarpsPerBlock = 8;
-constexpr int kGreedyLeaves = 4;   // leaves examined by the greedy phase-A bound
+#ifndef PLO_GREEDY_LEAVES
+#define PLO_GREEDY_LEAVES 2
+#endif
+constexpr int kGreedyLeaves = PLO_GREEDY_LEAVES;   // leaves examined by the greedy phase-A bound
 #ifndef PLO_MINB
 #define PLO_MINB 4
 #endif
@@ -211,7 +214,6 @@ __device__ __forceinline__ void rank_select(WarpScratch& ws, int C, int k, int l
   }
   __syncwarp();
 }
-
 
 // exact fp64 distances of the buffered candidates, libnabo's acceptance rule (unacceptable -> +inf)
 __device__ __forceinline__ void exact_distances(const MapView& m, WarpScratch& ws, int count, float qx, float qy, float qz,
@@ -389,6 +391,12 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
   }
   __syncwarp();
   st.n_cand = col.appended + 100000 * col.shrinks;
+  if (col.count > 32) {
+    // more than a warp's worth of candidates: a float k-th bound drops most of the surplus before
+    // the O(C^2 / 32) exact ranking
+    float Df = col.Df;
+    col.count = shrink_buffer(&ws, col.count, &Df, r2f_lo, allow_self ? 1 : 0, k);
+  }
   exact_distances(m, ws, col.count, qx, qy, qz, r2, allow_self, lane);
   rank_select(ws, col.count, k, lane);
   tk.d2 = ws.od2[lane];
@@ -457,13 +465,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
                                                                           const float4* __restrict__ sn,
                                                                           const DevCounts* __restrict__ counts,
                                                                           const DevState* __restrict__ st, DevParams P,
-                                                                          ProjectOut out, int hooks, int chunk,
+                                                                          ProjectOut out, int hooks, int chunk_arg,
                                                                           int* __restrict__ chunk_counter) {
   if (st->done) return;
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const int use_prev = st->use_prev;
+  const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
   // rPose rows (src/laser_odometry.cpp:530-535)
@@ -764,12 +773,13 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
   out.search_stats = c->q_stats.as<int>();
-  // chunk length: up to 4 consecutive queries per warp, fewer when the cloud is too small to fill
-  // the GPU; persistent grid (PLO_MINB blocks per SM), chunks fetched through an atomic counter
+  // persistent grid (PLO_MINB blocks per SM); chunks of consecutive source points are fetched through
+  // an atomic counter.  The chunk length comes from the device-side loop state (see k_solve_update)
+  // unless the cloud is too small to fill the GPU (then 1) or the tuning knob overrides it.
   const int64_t slots = (int64_t)plo_grid(c, PLO_MINB) * kWarpsPerBlock;
-  int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(4, c->m_raw / (2 * slots)));
-  if (const char* e = getenv("PLO_CHUNK")) chunk = std::max(1, atoi(e));   // tuning knob
-  const int64_t warps = (c->m_raw + chunk - 1) / chunk;
+  int chunk = (c->m_raw < 16 * slots) ? 1 : 0;
+  if (const char* e = getenv("PLO_CHUNK")) chunk = std::max(0, atoi(e));   // tuning knob (0 = device-side policy)
+  const int64_t warps = c->m_raw;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
   PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
   PLO_CUDA(c, cudaMemsetAsync(c->chunk_counter.p, 0, sizeof(int), c->stream));

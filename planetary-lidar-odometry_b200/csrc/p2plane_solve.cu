@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict_
   for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
   st->iters += 1;
   st->use_prev = 1;   // the projection just consumed left its k-th distances behind
+  // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
+  // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
+  st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
   if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
   else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
   if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
@@ -300,7 +303,7 @@ __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
     st->rank = 0;
     st->done = 0;
     st->use_prev = use_prev;
-    st->pad = 0;
+    st->chunk = use_prev ? PLO_CHUNK_MID : PLO_CHUNK_COLD;
   }
 }
 

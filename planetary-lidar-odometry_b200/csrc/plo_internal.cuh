@@ -18,6 +18,15 @@
 #define PLO_MAX_K 32              // neighbour list lives one entry per lane
 #define PLO_NSUM 36               // 21 H + 6 g + sw + swbb + count + 6 drop counters
 #define PLO_FULL_MASK 0xffffffffu
+#ifndef PLO_CHUNK_COLD
+#define PLO_CHUNK_COLD 8   // no temporal bound (first projection, or after a large pose step)
+#endif
+#ifndef PLO_CHUNK_MID
+#define PLO_CHUNK_MID 4    // previous projection available, step size unknown
+#endif
+#ifndef PLO_CHUNK_WARM
+#define PLO_CHUNK_WARM 1   // small pose step: temporal bound is tight
+#endif
 
 // ---------------------------------------------------------------------------------
 // device-side views
@@ -52,7 +61,7 @@ struct DevState {
   int rank;
   int done;       // kernels of later iterations return immediately when set
   int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds (temporal bound usable)
-  int pad;
+  int chunk;      // consecutive source points per warp in the next projection (carry bound vs. balance)
 };
 
 struct DevCounts {
