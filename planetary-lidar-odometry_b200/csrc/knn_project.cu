@@ -59,8 +59,12 @@ struct TopK {
   int pos;   // position in the sorted arrays (for gathers)
 };
 
+// traversal statistics; only carried by the hooks instantiation of the kernel
 struct SearchStats {
   int n_leaf, n_node, n_cand;
+  bool on;
+  __device__ __forceinline__ void leaf() { if (on) n_leaf++; }
+  __device__ __forceinline__ void node() { if (on) n_node++; }
 };
 
 struct WarpScratch {
@@ -71,6 +75,7 @@ struct WarpScratch {
   double od2[PLO_MAX_K];
   int oidx[PLO_MAX_K];
   int opos[PLO_MAX_K];
+  float new_Df;   // out-parameter of shrink_buffer (kept out of registers / local memory)
 };
 
 // ---- conservative fp32 geometry (directed rounding) ------------------------------------
@@ -151,7 +156,7 @@ struct Greedy {
   static __device__ __forceinline__ unsigned run(const MapView& m, int node, float qx, float qy, float qz, float r2f_lo,
                                                  bool allow_self, SearchStats& st, int lane) {
     const int child = node * PLO_FANOUT + lane;
-    st.n_node++;
+    st.node();
     // heuristic score (any choice is valid): squared distance to the box centre
     const float4 lo = __ldg(&m.lo[LEVEL - 1][child]), hi = __ldg(&m.hi[LEVEL - 1][child]);
     const float cx = qx - 0.5f * (lo.x + hi.x), cy = qy - 0.5f * (lo.y + hi.y), cz = qz - 0.5f * (lo.z + hi.z);
@@ -166,7 +171,7 @@ struct Greedy {
         const int c = __ffs(__ballot_sync(PLO_FULL_MASK, key == mn)) - 1;
         if (lane == c) key = 0xffffffffu;
         const float4 p = __ldg(&m.pts[(node * PLO_FANOUT + c) * PLO_LEAF + lane]);
-        st.n_leaf++;
+        st.leaf();
         const unsigned row = sort32_asc(bound_key(dist_lo2(qx, qy, qz, p), r2f_lo, allow_self), lane);
         best = (t == 0) ? row : merge32_low(best, row, lane);
       }
@@ -259,7 +264,7 @@ struct Collector {
 
 // buffer full: Df <- k-th smallest rounded-up distance among the buffered candidates that are
 // certainly acceptable; buffer compacted to lo <= Df.  Out of line: rare.
-__device__ __noinline__ int shrink_buffer(WarpScratch* ws, int count, float* Df_io, float r2f_lo, int allow_self, int k) {
+__device__ __noinline__ int shrink_buffer(WarpScratch* ws, int count, float Df, float r2f_lo, int allow_self, int k) {
   const int lane = threadIdx.x & 31;
   unsigned best = 0xffffffffu;
   for (int base = 0; base < count; base += 32) {
@@ -268,7 +273,6 @@ __device__ __noinline__ int shrink_buffer(WarpScratch* ws, int count, float* Df_
     const unsigned row = sort32_asc(key, lane);
     best = (base == 0) ? row : merge32_low(best, row, lane);
   }
-  float Df = *Df_io;
   const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
   if (kth < 0x7f800000u) Df = fminf(Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
   int kept = 0;
@@ -288,7 +292,8 @@ __device__ __noinline__ int shrink_buffer(WarpScratch* ws, int count, float* Df_
     kept += __popc(b);
     __syncwarp();
   }
-  *Df_io = Df;
+  if (lane == 0) ws->new_Df = Df;
+  __syncwarp();
   return kept;
 }
 
@@ -296,15 +301,14 @@ __device__ __forceinline__ void collect_leaf(const MapView& m, int leaf, float q
                                              bool allow_self, int k, WarpScratch& ws, Collector& col, SearchStats& st,
                                              int lane) {
   const float4 p = __ldg(&m.pts[leaf * PLO_LEAF + lane]);
-  st.n_leaf++;
+  st.leaf();
   const float lo = dist_lo2(qx, qy, qz, p);
   bool pass = lo <= col.Df;
   unsigned b = __ballot_sync(PLO_FULL_MASK, pass);
   if (b == 0u) return;
   if (col.count + __popc(b) > kCap) {
-    float Df = col.Df;
-    col.count = shrink_buffer(&ws, col.count, &Df, r2f_lo, allow_self ? 1 : 0, k);
-    col.Df = Df;
+    col.count = shrink_buffer(&ws, col.count, col.Df, r2f_lo, allow_self ? 1 : 0, k);
+    col.Df = ws.new_Df;
     col.shrinks++;
     pass = pass && (lo <= col.Df);
     b = __ballot_sync(PLO_FULL_MASK, pass);
@@ -334,7 +338,7 @@ struct Collect {
                                              bool allow_self, int k, WarpScratch& ws, Collector& col, SearchStats& st,
                                              int lane) {
     const int child = node * PLO_FANOUT + lane;
-    st.n_node++;
+    st.node();
     const float4 lo = __ldg(&m.lo[LEVEL - 1][child]), hi = __ldg(&m.hi[LEVEL - 1][child]);
     const float bd = box_lo2(qx, qy, qz, lo, hi);
     unsigned key = 0u;
@@ -390,12 +394,11 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
     Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
   }
   __syncwarp();
-  st.n_cand = col.appended + 100000 * col.shrinks;
+  if (st.on) st.n_cand = col.appended + 100000 * col.shrinks;
   if (col.count > 32) {
     // more than a warp's worth of candidates: a float k-th bound drops most of the surplus before
     // the O(C^2 / 32) exact ranking
-    float Df = col.Df;
-    col.count = shrink_buffer(&ws, col.count, &Df, r2f_lo, allow_self ? 1 : 0, k);
+    col.count = shrink_buffer(&ws, col.count, col.Df, r2f_lo, allow_self ? 1 : 0, k);
   }
   exact_distances(m, ws, col.count, qx, qy, qz, r2, allow_self, lane);
   rank_select(ws, col.count, k, lane);
@@ -410,6 +413,7 @@ template <int LEVELS>
 __device__ __noinline__ void knn1_noself(const MapView& m, float qx, float qy, float qz, double r2, WarpScratch* ws) {
   TopK tk;
   SearchStats st;
+  st.on = false;
   knn_topk<LEVELS>(m, qx, qy, qz, CUDART_INF_F, true, r2, 1, false, *ws, tk, st, threadIdx.x & 31);
 }
 
@@ -459,13 +463,13 @@ struct ProjectOut {
   int* search_stats;   // [M*3] leaves scanned, nodes expanded, candidates buffered (+ 100000 * shrinks)
 };
 
-template <bool PCA, int LEVELS>
+template <bool PCA, int LEVELS, bool HOOKS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const __grid_constant__ MapView m,
                                                                           const float4* __restrict__ sp,
                                                                           const float4* __restrict__ sn,
                                                                           const DevCounts* __restrict__ counts,
                                                                           const DevState* __restrict__ st, DevParams P,
-                                                                          ProjectOut out, int hooks, int chunk_arg,
+                                                                          ProjectOut out, int chunk_arg,
                                                                           int* __restrict__ chunk_counter) {
   if (st->done) return;
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
@@ -475,10 +479,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
-  // rPose rows (src/laser_odometry.cpp:530-535)
-  double T[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) T[i] = st->rPose[i];
+  // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
+  __shared__ double T[12];
+  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
+  __syncthreads();
 
   // Each warp walks chunks of `chunk` consecutive source points (handed out dynamically, one
   // atomic per chunk: per-query cost varies a lot).  Correctness never depends on the order of
@@ -532,6 +536,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
 
     TopK tk;
     SearchStats ss;
+    ss.on = HOOKS;
     if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane);   // :372-375 ALLOW_SELF_MATCH
     else { tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1; ss.n_leaf = ss.n_node = ss.n_cand = 0; }
     const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
       out.status[qi] = status;
       out.kd2f[qi] = kd2f_now;
     }
-    if (hooks) {
+    if constexpr (HOOKS) {
       if (lane < P.k) {
         out.nn_idx[(size_t)qi * P.k + lane] = has ? tk.idx : -1;
         out.nn_d2[(size_t)qi * P.k + lane] = has ? tk.d2 : CUDART_INF;
@@ -675,6 +680,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_pca_normals(const __gri
     if (isfinite(p.x)) {
       TopK tk;
       SearchStats ss;
+      ss.on = false;
       knn_topk<LEVELS>(m, p.x, p.y, p.z, CUDART_INF_F, true, P.r_normal2, P.k_normal, false, ws, tk, ss, lane);
       const bool has = (lane < P.k_normal) && (tk.d2 < CUDART_INF);
       const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, has));
@@ -743,8 +749,8 @@ int plo_launch_pca_normals(plo_ctx* c) {
 }
 
 namespace {
-template <bool PCA>
-void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int hooks, int chunk) {
+template <bool PCA, bool HOOKS>
+void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int chunk) {
   const MapView mv = c->map_view();
   const float4* sp = c->s_p.as<float4>();
   const float4* sn = c->s_n.as<float4>();
@@ -754,12 +760,12 @@ void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int ho
   const int T = kWarpsPerBlock * 32;
   switch (c->n_levels) {   // an empty map (n_levels == 0) never walks the tree: any instantiation does
     case 0:
-    case 1: k_project<PCA, 1><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
-    case 2: k_project<PCA, 2><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
-    case 3: k_project<PCA, 3><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
-    case 4: k_project<PCA, 4><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
-    case 5: k_project<PCA, 5><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
-    default: k_project<PCA, 6><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, hooks, chunk, cc); break;
+    case 1: k_project<PCA, 1, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
+    case 2: k_project<PCA, 2, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
+    case 3: k_project<PCA, 3, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
+    case 4: k_project<PCA, 4, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
+    case 5: k_project<PCA, 5, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
+    default: k_project<PCA, 6, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
   }
 }
 }  // namespace
@@ -783,8 +789,13 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
   PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
   PLO_CUDA(c, cudaMemsetAsync(c->chunk_counter.p, 0, sizeof(int), c->stream));
-  if (c->dprm.use_pca_normals) launch_project_levels<true>(c, blocks, out, hooks ? 1 : 0, chunk);
-  else launch_project_levels<false>(c, blocks, out, hooks ? 1 : 0, chunk);
+  if (c->dprm.use_pca_normals) {
+    if (hooks) launch_project_levels<true, true>(c, blocks, out, chunk);
+    else launch_project_levels<true, false>(c, blocks, out, chunk);
+  } else {
+    if (hooks) launch_project_levels<false, true>(c, blocks, out, chunk);
+    else launch_project_levels<false, false>(c, blocks, out, chunk);
+  }
   c->prev_valid = true;   // later projections of the same clouds may use this one's k-th distances
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
