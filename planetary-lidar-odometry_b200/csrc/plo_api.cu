@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -535,7 +536,9 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
   // iterations that are needed run, with no host round trip.  With per-launch profiling (or if the
   // driver refuses conditional nodes) every iteration is enqueued up front instead; kernels of
   // iterations after convergence then see the device-side `done` flag and return at once.
-  if (!c->profiling && c->graph_ok && c->m_raw > 0) {
+  // PLO_NO_GRAPH=1: enqueue-all path (ncu cannot profile kernel nodes of graphs with conditional nodes)
+  static const bool no_graph_env = getenv("PLO_NO_GRAPH") != nullptr && atoi(getenv("PLO_NO_GRAPH")) != 0;
+  if (!c->profiling && c->graph_ok && !no_graph_env && c->m_raw > 0) {
     if (!c->loop_exec || c->loop_sig != loop_signature(c)) {
       if (build_loop_graph(c) != 0) c->graph_ok = false;
     }
