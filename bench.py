@@ -103,6 +103,8 @@ def run_cpu(pair, steps, warmup, threads=0):
     """The reference arm / cpu_baseline: the oracle's full registration (kd-tree build + IMLS-ICP
     loop) with all host threads.  Returns (scans_per_s, ms_per_step, cores, pose, stats, detail)."""
     import oracle_ctypes as oc
+    if threads <= 0:   # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may use
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     orc = oc.Oracle(threads=threads)
     times, builds = [], []
     T = st = None
@@ -169,6 +171,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     pair = workload(1002 + rank, args.map_points)       # each rank registers its own frame (weak scaling)
@@ -200,7 +204,9 @@ def main():
 
     # ---- value: device-resident inputs, CUDA events on the context's stream --------------
     for _ in range(args.warmup):
-        step_device()
+        Tw, sw_ = step_device()
+    if world > 1 and args.warmup > 0:      # warm the communicator the end-of-run gather uses
+        plo.distributed.gather_results(plo.distributed.pack_result(Tw, sw_)[None, :], [rank], world, device=dev)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     idx_ms, reg_ms = [], []
