@@ -77,6 +77,24 @@ def hdl64_vs_map(seed: int = 1002, map_points: int = 1_000_000, voxel: float = 0
     return Pair(f"hdl64_vs_map{tgt.shape[0]}", _subsample(src, max_source, rng), tgt, np.linalg.inv(T_a) @ T_b)
 
 
+def hdl64_vs_dense_map(seed: int = 4001, map_points: int = 5_000_000, base_points: int = 1_000_000,
+                       jitter: float = 0.01) -> Pair:
+    """cfg-4 stress input: HDL-64 frame against a `map_points`-point accumulated map.  Ray casting 5 M
+    deduplicated points would take minutes, so the map is the `base_points` local map plus jittered
+    copies of it (sigma = `jitter` m, normals kept): same surfaces, 5x the density — the regime that
+    stresses the index build and the radius search."""
+    base = hdl64_vs_map(seed=seed, map_points=base_points)
+    rng = np.random.default_rng(seed + 7)
+    reps = int(np.ceil(map_points / base.target.shape[0]))
+    parts = [base.target]
+    for _ in range(reps - 1):
+        c = base.target.copy()
+        c[:, 0:3] += rng.normal(0.0, jitter, size=(c.shape[0], 3)).astype(np.float32)
+        parts.append(c)
+    tgt = np.concatenate(parts, axis=0)[:map_points]
+    return Pair(f"hdl64_vs_dense_map{tgt.shape[0]}", base.source, tgt, base.T_gt)
+
+
 def planetary_pair(seed: int = 3001, azimuth_steps: int = 1800) -> Pair:
     """cfg-3: sparse VLP-16 scans of fractal terrain with rocks (neighbour-starved path)."""
     rng = np.random.default_rng(seed)

@@ -449,3 +449,56 @@ def test_cpp_host_driver_matches_python_driver(tmp_path):
         got = np.loadtxt(out)
         assert got.shape == (3, 8)
         assert np.abs(got[:, 1:4] - P[:, :3, 3]).max() < 2e-6      # 6 decimals in the TUM file
+
+
+def test_cfg2_vlp32c_sequence_full_size(oracle_mod):
+    """BASELINE config 2 (VLP-32C-shaped sequence, IMLS matcher + weighted LS end to end), first frames at
+    full size: per-frame pose parity with the oracle and closeness to the ground-truth motion."""
+    seq = W.Sequence(seed=2001, n_frames=4)
+    frames = [seq.frame(k) for k in range(4)]
+    assert 40000 < frames[0].shape[0] < 70000
+    odo = plo.LaserOdometry(resident=True)
+    odo.run(frames)
+    orc = oracle_mod.Oracle()
+    for k in range(1, 4):
+        orc.set_target(frames[k - 1])
+        orc.set_source(frames[k])
+        To, so = orc.register()
+        st = odo.frame_stats[k]
+        assert st["iters"] == so["iters"] and st["status"] == so["status"] and st["pairs"] == so["pairs"]
+        assert _rot_err(st["rPose"][:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(st["rPose"][:3, 3] - To[:3, 3]) < POSE_M
+        gt = seq.relative_gt(k)
+        assert np.linalg.norm(st["rPose"][:3, 3] - gt[:3, 3]) < 0.05 and _rot_err(st["rPose"][:3, :3], gt[:3, :3]) < 5e-3
+
+
+def test_cfg4_five_million_point_map(oracle_mod):
+    """BASELINE config 4 (HDL-64 frame vs 5 M-point map: index build + radius-search stress, 4 tree levels):
+    iteration-0 neighbour sets against the oracle on a query subset, full-loop pose parity, index-size properties."""
+    pair = W.hdl64_vs_dense_map()
+    assert pair.target.shape[0] == 5_000_000
+    sub = pair.source[::8]
+    ctx, orc = _both(oracle_mod, pair.target, sub)
+    assert ctx.n_target == 5_000_000
+    g, o = _check_projection(ctx, orc)
+    Tg, sg = ctx.register()
+    To, so = orc.register()
+    assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    # the full frame on the same index: converges to the same place as the subset (size-independent property)
+    ctx.set_source(pair.source)
+    Tf, sf = ctx.register()
+    assert sf["status"] == 1 and np.linalg.norm(Tf[:3, 3] - Tg[:3, 3]) < 5e-3
+    assert np.linalg.norm(Tf[:3, 3] - pair.T_gt[:3, 3]) < 0.02
+
+
+def test_cfg5_batched_sequences_single_rank(oracle_mod):
+    """BASELINE config 5 on one rank: the sharded driver (one plo_register_batch per sequence, gather, pose
+    chaining) reproduces frame-by-frame registration bit for bit."""
+    seqs = [W.Sequence(seed=5000 + s, n_frames=3, max_points=8000) for s in range(3)]
+    ctx = plo.Context(0)
+    trajs, table = plo.distributed.register_sequences_sharded(ctx, seqs)
+    assert table.shape == (9, plo.distributed.RESULT_WIDTH)
+    for s, seq in enumerate(seqs):
+        odo = plo.LaserOdometry(resident=True)
+        P = odo.run([seq.frame(k) for k in range(3)])
+        assert np.array_equal(P, trajs[s])
