@@ -159,7 +159,7 @@ void plo_destroy(plo_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->t_stage, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
+  DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
                     &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
@@ -171,6 +171,9 @@ void plo_destroy(plo_ctx* c) {
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->ev_proj) cudaEventDestroy(e);
   destroy_loop_graph(c);
+  for (int i = 0; i < 2; ++i) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
+  if (c->ev_batch_start) cudaEventDestroy(c->ev_batch_start);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -651,10 +654,52 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   PLO_CUDA(c, cudaMallocHost(&h_slots, sizeof(DevState) * (size_t)count));
   int rc = PLO_OK;
   int graph_units = 0;
+  // Host inputs: double-buffered staging on a second stream, so that the upload of pair i+1 overlaps
+  // the registration of pair i (pinned host memory makes the copies truly asynchronous).
+  DevBuf* stage_t[2] = {&c->t_stage, &c->t_stage2};
+  DevBuf* stage_s[2] = {&c->s_stage, &c->s_stage2};
+  if (!on_device) {
+    if (stride < 28 || (stride % 4) != 0) { cudaFreeHost(h_slots); slots.release(); return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad stride"); }
+    int64_t max_t = 1, max_s = 1;
+    for (int i = 0; i < count; ++i) {
+      if (n_tgt[i] < 0 || n_src[i] < 0 || (n_tgt[i] > 0 && !targets[i]) || (n_src[i] > 0 && !sources[i])) {
+        cudaFreeHost(h_slots); slots.release();
+        return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad pointer / count");
+      }
+      max_t = std::max(max_t, n_tgt[i]);
+      max_s = std::max(max_s, n_src[i]);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      e = stage_t[b]->reserve((size_t)max_t * stride);
+      if (e == cudaSuccess) e = stage_s[b]->reserve((size_t)max_s * stride);
+      if (e == cudaSuccess && !c->ev_copied[b]) e = cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming);
+      if (e == cudaSuccess && !c->ev_consumed[b]) e = cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess && !c->ev_batch_start) e = cudaEventCreateWithFlags(&c->ev_batch_start, cudaEventDisableTiming);
+    if (e == cudaSuccess && !c->copy_stream) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    // earlier work on the main stream may still read the staging buffers
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_batch_start, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_batch_start, 0);
+    if (e != cudaSuccess) { cudaFreeHost(h_slots); slots.release(); return plo_fail(c, PLO_ERR_CUDA, std::string("plo_register_batch: ") + cudaGetErrorString(e)); }
+  }
   for (int i = 0; i < count && rc == PLO_OK; ++i) {
-    // the staging buffers are reused pair after pair: stream order keeps that safe
-    rc = on_device ? plo_set_target_device(c, targets[i], n_tgt[i], stride) : plo_set_target(c, targets[i], n_tgt[i], stride);
-    if (rc == PLO_OK) rc = on_device ? plo_set_source_device(c, sources[i], n_src[i], stride) : plo_set_source(c, sources[i], n_src[i], stride);
+    if (on_device) {
+      rc = plo_set_target_device(c, targets[i], n_tgt[i], stride);
+      if (rc == PLO_OK) rc = plo_set_source_device(c, sources[i], n_src[i], stride);
+    } else {
+      const int b = i & 1;
+      cudaError_t e = cudaSuccess;
+      if (i >= 2) e = cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0);   // pair i-2 has unpacked this buffer
+      if (e == cudaSuccess && n_tgt[i] > 0) e = cudaMemcpyAsync(stage_t[b]->p, targets[i], (size_t)n_tgt[i] * stride, cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess && n_src[i] > 0) e = cudaMemcpyAsync(stage_s[b]->p, sources[i], (size_t)n_src[i] * stride, cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(c->ev_copied[b], c->copy_stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0);
+      if (e != cudaSuccess) { rc = plo_fail(c, PLO_ERR_CUDA, std::string("plo_register_batch: ") + cudaGetErrorString(e)); break; }
+      rc = plo_build_index(c, stage_t[b]->p, n_tgt[i], stride);
+      if (rc == PLO_OK) rc = plo_upload_source(c, stage_s[b]->p, n_src[i], stride);
+      if (rc == PLO_OK && cudaEventRecord(c->ev_consumed[b], c->stream) != cudaSuccess) rc = plo_fail(c, PLO_ERR_CUDA, "plo_register_batch: event record failed");
+    }
     if (rc == PLO_OK) rc = enqueue_register(c, nullptr);
     if (rc == PLO_OK) {
       if (c->graph_launched) { graph_units++; c->graph_launched = false; }
@@ -670,6 +715,7 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   } else {
     cudaStreamSynchronize(c->stream);
   }
+  if (!on_device && c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (rc == PLO_OK) {
     for (int i = 0; i < count; ++i) {
       if (graph_units > 0) c->launches += 3 * (int64_t)(h_slots[i].iters + (h_slots[i].status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0));

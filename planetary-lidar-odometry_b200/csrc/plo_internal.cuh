@@ -111,7 +111,7 @@ struct plo_ctx {
   bool pca_valid = false;
   int n_levels = 0;
   int64_t level_nodes[PLO_MAX_LEVELS] = {0};
-  DevBuf t_stage, t_praw, t_nraw, t_cidx, blockcnt, bbox;
+  DevBuf t_stage, t_stage2, t_praw, t_nraw, t_cidx, blockcnt, bbox;
   DevBuf keys[2], vals[2], hist, digit_total;
   DevBuf pts_sorted, nrm_sorted, nrm_pca, pos_of_cidx;
   DevBuf lvl_lo[PLO_MAX_LEVELS], lvl_hi[PLO_MAX_LEVELS];
@@ -119,7 +119,7 @@ struct plo_ctx {
   // source
   int64_t m_raw = 0;
   bool have_source = false;
-  DevBuf s_stage, s_praw, s_nraw, s_p, s_n;
+  DevBuf s_stage, s_stage2, s_praw, s_nraw, s_p, s_n;
 
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
@@ -141,6 +141,9 @@ struct plo_ctx {
   cudaGraph_t loop_graph = nullptr;
   cudaGraphExec_t loop_exec = nullptr;
   std::vector<unsigned long long> loop_sig;
+  // batched mode: host->device copies of pair i+1 overlap the registration of pair i
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_batch_start = nullptr;
   bool graph_launched = false;   // the last enqueue_register went through the graph
   bool graph_ok = true;      // cleared if the driver rejects conditional nodes: falls back to enqueue-all
   bool profiling = false;
