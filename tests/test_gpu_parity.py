@@ -502,3 +502,51 @@ def test_cfg5_batched_sequences_single_rank(oracle_mod):
         odo = plo.LaserOdometry(resident=True)
         P = odo.run([seq.frame(k) for k in range(3)])
         assert np.array_equal(P, trajs[s])
+
+
+def test_randomised_small_clouds_fuzz(oracle_mod):
+    """Randomised parity sweep: cloud sizes around the leaf / level boundaries, clustered and
+    grid-quantised coordinates (many exact ties and duplicates), random k / r / h / angle gate,
+    sprinkled NaNs and zero normals — neighbour sets, statuses and counters must match the oracle
+    exactly for every draw."""
+    rng = np.random.default_rng(20240607)
+    sizes = [1, 2, 3, 19, 20, 21, 31, 32, 33, 63, 64, 65, 500, 1023, 1024, 1025, 1500, 4000, 33000]
+    for trial in range(48):
+        n_t = int(rng.choice(sizes))
+        n_s = int(rng.choice([1, 5, 33, 200, 700]))
+        mode = trial % 4
+        if mode == 0:      # uniform
+            xyz = rng.uniform(-3, 3, size=(n_t, 3))
+        elif mode == 1:    # quantised grid: exact ties and duplicates
+            xyz = np.round(rng.uniform(-2, 2, size=(n_t, 3)) * 4) / 4
+        elif mode == 2:    # tight clusters + far outliers
+            c = rng.uniform(-20, 20, size=(max(1, n_t // 50), 3))
+            xyz = c[rng.integers(0, c.shape[0], n_t)] + rng.normal(0, 0.05, size=(n_t, 3))
+        else:              # thin surface (plane with noise)
+            xyz = np.concatenate([rng.uniform(-5, 5, size=(n_t, 2)), rng.normal(0, 0.01, size=(n_t, 1))], axis=1)
+        tgt = np.zeros((n_t, 12), np.float32)
+        tgt[:, 0:3] = xyz
+        nrm = rng.normal(size=(n_t, 3)) * [0.3, 0.3, 1.0]
+        nrm[:, 2] = np.abs(nrm[:, 2])
+        tgt[:, 4:7] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+        src = np.zeros((n_s, 12), np.float32)
+        pick = rng.integers(0, n_t, n_s)
+        src[:, 0:3] = xyz[pick] + rng.normal(0, rng.choice([0.0, 0.02, 0.5]), size=(n_s, 3))
+        src[:, 4:7] = tgt[pick, 4:7]
+        if trial % 5 == 0 and n_t > 3:
+            tgt[rng.integers(0, n_t, 2), rng.integers(0, 3, 2)] = np.nan
+            tgt[rng.integers(0, n_t), 4:7] = 0
+            src[rng.integers(0, n_s), 4:7] = 0
+        kw = dict(search_number=int(rng.choice([1, 3, 10, 20, 32])), r=float(rng.choice([0.2, 1.0, 3.0, 10.0])),
+                  h=float(rng.choice([0.1, 1.0, 5.0])), angle_diff_threshold=float(rng.choice([5.0, 30.0, 90.0, 200.0])),
+                  normal_angle_constraint=int(rng.integers(0, 2)))
+        ctx, orc = _both(oracle_mod, tgt, src, **kw)
+        T = plo.synth.scenes.pose_matrix(rng.normal(0, 0.05, 3), yaw_deg=rng.normal(0, 2)) if trial % 3 else np.eye(4)
+        try:
+            _check_projection(ctx, orc, T=T)
+            # a second projection at a nearby pose exercises the temporal bound
+            T2 = plo.synth.scenes.pose_matrix(rng.normal(0, 0.01, 3), yaw_deg=rng.normal(0, 0.2)) @ T
+            _check_projection(ctx, orc, T=T2)
+        except AssertionError as e:
+            raise AssertionError(f"trial {trial}: n_t={n_t} n_s={n_s} mode={mode} {kw}: {e}") from e
+        ctx.close()
