@@ -67,6 +67,12 @@ typedef enum plo_reg_status {
   PLO_REG_SOLVE_FAILED = 4   /* :611-616 (no pivot at all: every pair had a zero row) */
 } plo_reg_status;
 
+typedef enum plo_solver {
+  PLO_SOLVER_WLS = 0, /* SolveMotionEstimationProblemWeightedLS, src/solver.cpp:168-220 (default)      */
+  PLO_SOLVER_LS = 1   /* SolveMotionEstimationProblemLS, src/solver.cpp:74-166: LS, then a second LS on  */
+                      /* the pairs whose |residual| rank lies in [thr*N, (1-thr)*N] (2 % / 98 % trim)    */
+} plo_solver;
+
 typedef enum plo_weight_mode {
   PLO_W_UNIT = 0,     /* plain point-to-plane LS (weights = 1)                         */
   PLO_W_HUBER_EXP = 1 /* RANSAC-final weights of src/solver.cpp:334-364 at T_best = I  */
@@ -93,6 +99,8 @@ typedef struct plo_params {
   int32_t weight_mode;             /* plo_weight_mode                                  0 */
   double ransac_distance_threshold;/* RANSAC.distance_threshold (PLO_W_HUBER_EXP)    0.8 */
   double huber_threshold;          /* RANSAC.huber_threshold    (PLO_W_HUBER_EXP)  0.648 */
+  int32_t solver;                  /* plo_solver                                       0 */
+  double ls_threshold;             /* solve_method.LS.threshold (PLO_SOLVER_LS)     0.02 */
 } plo_params;
 
 typedef struct plo_proj_stats {
@@ -177,6 +185,10 @@ PLO_API int plo_get_target_normals(plo_ctx* ctx, double* out);
  * context's weight_mode.  delta = deltaTrans (row-major).  Returns PLO_OK also when the
  * system is rank-deficient (the reference always returns true); *rank (nullable) tells. */
 PLO_API int plo_solve_wls(plo_ctx* ctx, double delta[16], int32_t* rank);
+/* plo_solve_ls == SolveMotionEstimationProblemLS (src/solver.cpp:74-166, include/solver.h:84-90) on the
+ * device-resident pairs of the last plo_project, trim fraction = params.ls_threshold.  Ties in the
+ * |residual| order are broken by pair index (std::sort there is unstable). */
+PLO_API int plo_solve_ls(plo_ctx* ctx, double delta[16], int32_t* rank);
 /* same solver, reference-shaped inputs: host arrays of n x 3 doubles + n weights
  * (NULL = unit) — the argument list of SolveMotionEstimationProblemWeightedLS */
 PLO_API int plo_solve_wls_host(plo_ctx* ctx, const double* src, const double* ref,

@@ -9,7 +9,9 @@ only prints, :567 and :271).
 Accepted selections
   matching_method.method : "IMLS" (with top-level "backend": "cuda", the default here) or
                            "IMLS_CUDA"
-  solve_method.method    : "WeightedLS_CUDA", "Weighted LS", "LS_CUDA" (unit weights), or
+  solve_method.method    : "WeightedLS_CUDA" / "Weighted LS" (weighted LS, unit weights unless
+                           "weights": "huber_exp"), "LS" / "LS_CUDA" (the reference's trimmed LS,
+                           src/solver.cpp:74-166, threshold from solve_method.LS.threshold), or
                            "RANSAC" with final_solve_method "Weighted LS" (mapped to the
                            RANSAC-final Huber/exp weights evaluated at T_best = I)
 Everything else the reference lists (plane_ICP, Ceres, ICP, Teaser, RANSAC->DRPM/LS,
@@ -46,6 +48,7 @@ DEFAULT_CONFIG = {
             "iterations": 30,
             "delta_dist_threshold": 0.001,
             "delta_angle_threshold": 0.0001745353,
+            "LS": {"threshold": 0.02},
             "RANSAC": {"distance_threshold": 0.8, "huber_threshold": 0.648, "final_solve_method": "Weighted LS"},
         },
     },
@@ -96,15 +99,18 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
     sm = _get(lo, "solve_method")
     smethod = _get(sm, "method")
     weight_mode = _lib.W_UNIT
-    if smethod in ("WeightedLS_CUDA", "Weighted LS", "LS_CUDA"):
+    solver = _lib.SOLVER_WLS
+    if smethod in ("WeightedLS_CUDA", "Weighted LS"):
         weight_mode = _lib.W_HUBER_EXP if _get(sm, "weights", default="unit", required=False) == "huber_exp" else _lib.W_UNIT
+    elif smethod in ("LS", "LS_CUDA"):
+        solver = _lib.SOLVER_LS
     elif smethod == "RANSAC":
         final = _get(sm, "RANSAC", "final_solve_method")
         if final != "Weighted LS":
             raise ConfigError(f'solve_method RANSAC -> "{final}" is a "next" row (SURVEY.md §8f); '
                               'only final_solve_method "Weighted LS" maps onto the device solver')
         weight_mode = _lib.W_HUBER_EXP
-    elif smethod in ("Ceres", "LS", "ICP", "Teaser"):
+    elif smethod in ("Ceres", "ICP", "Teaser"):
         raise ConfigError(f'solve_method "{smethod}" is outside the hot-path scope (SURVEY.md §2.1 row 2)')
     else:
         raise ConfigError(f"Invalid SOLVE_METHOD! ({smethod!r})")
@@ -125,4 +131,6 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
         weight_mode=weight_mode,
         ransac_distance_threshold=float(rs.get("distance_threshold", 0.8)),
         huber_threshold=float(rs.get("huber_threshold", 0.648)),
+        solver=solver,
+        ls_threshold=float((_get(sm, "LS", default={}, required=False) or {}).get("threshold", 0.02)),
     )

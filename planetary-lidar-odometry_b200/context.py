@@ -163,6 +163,13 @@ class Context:
         self._ck(self.L.plo_solve_wls(self.h, _ptr(d), C.byref(rank)))
         return d.reshape(4, 4), rank.value
 
+    def solve_ls(self):
+        """SolveMotionEstimationProblemLS (trimmed) on the pairs of the last projection"""
+        d = np.empty(16, np.float64)
+        rank = C.c_int32()
+        self._ck(self.L.plo_solve_ls(self.h, _ptr(d), C.byref(rank)))
+        return d.reshape(4, 4), rank.value
+
     def solve_wls_host(self, src, ref, nrm, w=None):
         src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
         w = None if w is None else np.ascontiguousarray(w, np.float64)

@@ -500,6 +500,33 @@ int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stri
   return PLO_OK;
 }
 
+// Stable LSD radix sort of n (u64 key, i32 value) pairs on the context's stream: `passes` 10-bit digits
+// starting at bit 0.  keys[0]/vals[0] hold the input; returns the index (0/1) of the buffers that hold
+// the sorted output.  hist must hold kRadix * ceil(n / 4096) ints, digit_total `passes` * kRadix ints.
+int plo_sort_pairs(plo_ctx* c, unsigned long long* keys[2], int* vals[2], int64_t n, int passes, int* hist, int* digit_total,
+                   int* out_which) {
+  const int nbs = (int)((n + kSortTile - 1) / kSortTile);
+  cudaStream_t s = c->stream;
+  PLO_CUDA(c, cudaMemsetAsync(digit_total, 0, sizeof(int) * (size_t)passes * kRadix, s));
+  int cur = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * kRadixBits;
+    int* tot = digit_total + pass * kRadix;
+    k_sort_hist<<<nbs, 256, 0, s>>>(keys[cur], (int)n, shift, nbs, hist, tot);
+    LAUNCH_CHECK(c);
+    k_sort_scan<<<kRadix, 256, 0, s>>>(hist, nbs, tot);
+    LAUNCH_CHECK(c);
+    k_sort_scatter<<<nbs, 256, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], (int)n, shift, nbs, hist);
+    LAUNCH_CHECK(c);
+    cur ^= 1;
+  }
+  *out_which = cur;
+  return PLO_OK;
+}
+
+size_t plo_sort_hist_ints(int64_t n) { return (size_t)kRadix * (size_t)((n + kSortTile - 1) / kSortTile); }
+size_t plo_sort_total_ints(int passes) { return (size_t)passes * kRadix; }
+
 int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride) {
   c->have_source = false;
   c->projected = false;

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
                                                                  const float4* __restrict__ qn,
                                                                  const DevCounts* __restrict__ counts,
                                                                  const DevState* __restrict__ st, DevParams P,
-                                                                 double* __restrict__ partials, int respect_done) {
+                                                                 double* __restrict__ partials, int respect_done,
+                                                                 const int* __restrict__ mask) {
   if (respect_done && st->done) return;
   double acc[PLO_NSUM];
 #pragma unroll
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
     const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
     const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
     acc[29] += 1.0;
+    if (mask != nullptr && mask[i] == 0) continue;   // trimmed LS, second pass: pair outside the kept rank window
     double w = 1.0;
     if (P.weight_mode == PLO_W_HUBER_EXP) {
       w = huber_exp_weight(s, d, n, P);
@@ -215,7 +217,10 @@ __device__ int solve_ldlt6(const double H21[21], const double g[6], double count
 }
 
 __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
-                                                       DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond) {
+                                                       DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond,
+                                                       int stage) {
+  // stage 0: weighted LS (one pass).  Trimmed LS (src/solver.cpp:74-166): stage 1 = first solve on all pairs,
+  // only x0 is kept (:107); stage 2 = second solve on the pairs selected by residual rank (:137) + loop tail.
   if (advance_loop && st->done) {
     if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
     return;
@@ -240,9 +245,11 @@ __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict_
   for (int i = 0; i < 6; ++i) st->g[i] = s_sum[21 + i];
   st->sw = sw;
   st->swbb = s_sum[28];
-  st->pairs = (long long)count;
-  for (int i = 0; i < 6; ++i) st->dropped[i] = (long long)s_sum[30 + i];
-  st->rms = count > 0.0 ? sqrt(s_sum[28] / fmax(sw, 1e-300)) : 0.0;
+  if (stage != 2) {   // the statistics describe the projection, not the trimmed subset
+    st->pairs = (long long)count;
+    for (int i = 0; i < 6; ++i) st->dropped[i] = (long long)s_sum[30 + i];
+    st->rms = count > 0.0 ? sqrt(s_sum[28] / fmax(sw, 1e-300)) : 0.0;
+  }
   if (advance_loop && count < (double)P.correspond_number) {   // src/laser_odometry.cpp:570-576
     st->status = PLO_REG_TOO_FEW_PAIRS;
     st->done = 1;
@@ -255,8 +262,12 @@ __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict_
   for (int i = 0; i < 21; ++i) H[i] = s_sum[i] * scale;
   for (int i = 0; i < 6; ++i) g[i] = s_sum[21 + i] * scale;
   double x[6];
-  const int rank = solve_ldlt6(H, g, count, x);
+  const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
   st->rank = rank;
+  if (stage == 1) {
+    for (int i = 0; i < 6; ++i) st->x0[i] = x[i];
+    return;   // the loop condition keeps its value (1): the body goes on with the selection
+  }
   double R[9];
   rodrigues(x, R);
   polar_orthogonalize(R);
@@ -287,6 +298,52 @@ __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict_
   if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
 }
 
+// trimmed LS: |A_i x0 - b_i| of every surviving pair as a sortable 64-bit key (src/solver.cpp:110-122);
+// dropped points and the padding sort last.  Ties keep the pair order (stable sort, value = index).
+__global__ void __launch_bounds__(256) k_ls_keys(const float4* __restrict__ qx, const float4* __restrict__ qy,
+                                                 const float4* __restrict__ qn, const DevCounts* __restrict__ counts,
+                                                 const DevState* __restrict__ st, int respect_done, int m_raw,
+                                                 unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  if (respect_done && st->done) return;
+  const int n_src = counts->n_source;
+  double x0[6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) x0[a] = st->x0[a];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m_raw; i += gridDim.x * blockDim.x) {
+    unsigned long long key = 0xffffffffffffffffull;
+    if (i < n_src) {
+      const float4 x = __ldg(&qx[i]);
+      if (__float_as_int(x.w) == PLO_PT_OK) {
+        const float4 y = __ldg(&qy[i]);
+        const float4 nn = __ldg(&qn[i]);
+        const double s[3] = {(double)x.x, (double)x.y, (double)x.z};
+        const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
+        const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
+        double a[6], b;
+        ab_row(s, d, n, a, b);
+        double r = 0.0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) r += a[t] * x0[t];
+        key = (unsigned long long)__double_as_longlong(fabs(r - b));   // non-negative doubles order like their bits
+      }
+    }
+    keys[i] = key;
+    vals[i] = i;
+  }
+}
+
+// rank window [thr*N, (1-thr)*N] of the sorted pairs -> per-source-point mask (src/solver.cpp:124-134)
+__global__ void __launch_bounds__(256) k_ls_select(const int* __restrict__ vals_sorted, const DevState* __restrict__ st,
+                                                   int respect_done, int m_raw, double threshold, int* __restrict__ mask) {
+  if (respect_done && st->done) return;
+  const long long N = st->pairs;
+  const long long lower = (long long)(threshold * (double)N);
+  long long upper = (long long)((1.0 - threshold) * (double)N);
+  if (upper > N - 1) upper = N - 1;   // the reference reads one past the end at threshold = 0
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m_raw; j += gridDim.x * blockDim.x)
+    mask[vals_sorted[j]] = (j >= lower && j <= upper) ? 1 : 0;
+}
+
 __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 16; ++i) {
@@ -295,7 +352,7 @@ __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
       st->delta[i] = id;
     }
     for (int i = 0; i < 21; ++i) st->H[i] = 0.0;
-    for (int i = 0; i < 6; ++i) { st->g[i] = 0.0; st->dropped[i] = 0; }
+    for (int i = 0; i < 6; ++i) { st->g[i] = 0.0; st->dropped[i] = 0; st->x0[i] = 0.0; }
     st->sw = st->swbb = st->rms = st->delta_dist = st->delta_angle = 0.0;
     st->pairs = 0;
     st->iters = 0;
@@ -381,18 +438,65 @@ int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null) {
   return PLO_OK;
 }
 
+constexpr int kLsPasses = 7;   // 64-bit keys, 10-bit digits
+
+int plo_reserve_solver_buffers(plo_ctx* c) {
+  PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
+  if (c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0) {
+    const size_t m = (size_t)c->m_raw;
+    for (int a = 0; a < 2; ++a) {
+      PLO_CUDA(c, c->ls_keys[a].reserve(sizeof(unsigned long long) * m));
+      PLO_CUDA(c, c->ls_vals[a].reserve(sizeof(int) * m));
+    }
+    PLO_CUDA(c, c->ls_hist.reserve(sizeof(int) * plo_sort_hist_ints(c->m_raw)));
+    PLO_CUDA(c, c->ls_tot.reserve(sizeof(int) * plo_sort_total_ints(kLsPasses)));
+    PLO_CUDA(c, c->ls_mask.reserve(sizeof(int) * m));
+  }
+  return PLO_OK;
+}
+
 int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long cond_handle) {
   const int g = reduce_grid(c, c->m_raw);
-  PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
+  PLO_TRY(plo_reserve_solver_buffers(c));
+  const int adv = advance_loop ? 1 : 0;
+  const cudaGraphConditionalHandle cond = (cudaGraphConditionalHandle)cond_handle;
+  const int use_cond = cond_handle ? 1 : 0;
+  const bool trimmed = c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0;
+  DevParams P = c->dprm;
+  if (trimmed) P.weight_mode = PLO_W_UNIT;   // SolveMotionEstimationProblemLS is unweighted
   if (c->m_raw > 0) {
     k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
-                                                        c->counts.as<DevCounts>(), c->state.as<DevState>(), c->dprm,
-                                                        c->partials.as<double>(), advance_loop ? 1 : 0);
+                                                        c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
+                                                        c->partials.as<double>(), adv, nullptr);
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
   }
-  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), c->dprm,
-                                            advance_loop ? 1 : 0, (cudaGraphConditionalHandle)cond_handle, cond_handle ? 1 : 0);
+  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), P, adv, cond,
+                                            use_cond, trimmed ? 1 : 0);
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  if (!trimmed) return PLO_OK;
+  // ---- trimmed LS: residual keys -> stable sort -> rank window -> second reduce + solve ----
+  const int m = (int)c->m_raw;
+  const int gk = (int)std::max<int64_t>(1, std::min<int64_t>((m + 255) / 256, (int64_t)plo_grid(c, 4)));
+  k_ls_keys<<<gk, 256, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(), c->counts.as<DevCounts>(),
+                                       c->state.as<DevState>(), adv, m, c->ls_keys[0].as<unsigned long long>(),
+                                       c->ls_vals[0].as<int>());
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  unsigned long long* keys[2] = {c->ls_keys[0].as<unsigned long long>(), c->ls_keys[1].as<unsigned long long>()};
+  int* vals[2] = {c->ls_vals[0].as<int>(), c->ls_vals[1].as<int>()};
+  int which = 0;
+  PLO_TRY(plo_sort_pairs(c, keys, vals, m, kLsPasses, c->ls_hist.as<int>(), c->ls_tot.as<int>(), &which));
+  k_ls_select<<<gk, 256, 0, c->stream>>>(vals[which], c->state.as<DevState>(), adv, m, c->dprm.ls_threshold, c->ls_mask.as<int>());
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
+                                                      c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
+                                                      c->partials.as<double>(), adv, c->ls_mask.as<int>());
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond, 2);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
@@ -410,7 +514,7 @@ int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const do
   DevParams P = c->dprm;
   P.weight_mode = PLO_W_UNIT;   // caller-supplied weights are used as they are
   k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), n > 0 ? g : 0, c->state.as<DevState>(), P, 0,
-                                            (cudaGraphConditionalHandle)0, 0);
+                                            (cudaGraphConditionalHandle)0, 0, 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;

@@ -81,6 +81,8 @@ static void flatten_params(plo_ctx* c) {
   d.correspond_number = p.correspond_number;
   d.weight_mode = p.weight_mode;
   d.iterations = p.iterations;
+  d.solver = p.solver;
+  d.ls_threshold = p.ls_threshold;
 }
 
 extern "C" {
@@ -106,6 +108,8 @@ void plo_default_params(plo_params* p) {
   p->weight_mode = PLO_W_UNIT;
   p->ransac_distance_threshold = 0.8;      // :146
   p->huber_threshold = 0.648;              // :148
+  p->solver = PLO_SOLVER_WLS;
+  p->ls_threshold = 0.02;                  // :141
 }
 
 int plo_create(int device, plo_ctx** out) {
@@ -163,7 +167,7 @@ void plo_destroy(plo_ctx* c) {
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
                     &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
-                    &c->counts, &c->scratch, &c->chunk_counter, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
+                    &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
   if (c->h_state) cudaFreeHost(c->h_state);
@@ -209,6 +213,10 @@ int plo_set_params(plo_ctx* c, const plo_params* p) {
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: h, r, r_normal must be >= 0");
   if (p->weight_mode != PLO_W_UNIT && p->weight_mode != PLO_W_HUBER_EXP)
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown weight_mode");
+  if (p->solver != PLO_SOLVER_WLS && p->solver != PLO_SOLVER_LS)
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown solver");
+  if (p->solver == PLO_SOLVER_LS && !(p->ls_threshold >= 0.0 && p->ls_threshold < 0.5))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: ls_threshold must be in [0, 0.5)");
   const bool pca_changed = c->prm.r_normal != p->r_normal || c->prm.search_number_normal != p->search_number_normal ||
                            c->prm.is_get_normals != p->is_get_normals;
   c->prm = *p;
@@ -300,7 +308,11 @@ int plo_project(plo_ctx* c, const double T[16], int32_t hooks, plo_proj_stats* s
   c->hooks_valid = hooks != 0;
   if (stats) {
     // the drop counters come out of the same reduction the solver uses
-    PLO_TRY(plo_launch_reduce_solve(c, false));
+    const int saved_solver = c->dprm.solver;
+    c->dprm.solver = PLO_SOLVER_WLS;
+    const int rrc = plo_launch_reduce_solve(c, false);
+    c->dprm.solver = saved_solver;
+    PLO_TRY(rrc);
     PLO_TRY(fetch_state(c));
     stats->n_source = c->h_counts->n_source;
     stats->n_pairs = c->h_state->pairs;
@@ -421,16 +433,24 @@ int plo_get_target_normals(plo_ctx* c, double* out) {
   return PLO_OK;
 }
 
-int plo_solve_wls(plo_ctx* c, double delta[16], int32_t* rank) {
-  if (!c || !delta) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_wls: NULL argument");
-  if (!c->projected) return plo_fail(c, PLO_ERR_STATE, "plo_solve_wls: call plo_project first");
+static int solve_on_pairs(plo_ctx* c, double delta[16], int32_t* rank, int solver, const char* who) {
+  if (!c || !delta) return plo_fail(c, PLO_ERR_INVALID_ARG, std::string(who) + ": NULL argument");
+  if (!c->projected) return plo_fail(c, PLO_ERR_STATE, std::string(who) + ": call plo_project first");
   PLO_CUDA(c, cudaSetDevice(c->device));
-  PLO_TRY(plo_launch_reduce_solve(c, false));
+  const int saved = c->dprm.solver;
+  c->dprm.solver = solver;
+  const int rc = plo_launch_reduce_solve(c, false);
+  c->dprm.solver = saved;
+  PLO_TRY(rc);
   PLO_TRY(fetch_state(c));
   memcpy(delta, c->h_state->delta, sizeof(double) * 16);
   if (rank) *rank = c->h_state->rank;
   return PLO_OK;
 }
+
+int plo_solve_wls(plo_ctx* c, double delta[16], int32_t* rank) { return solve_on_pairs(c, delta, rank, PLO_SOLVER_WLS, "plo_solve_wls"); }
+
+int plo_solve_ls(plo_ctx* c, double delta[16], int32_t* rank) { return solve_on_pairs(c, delta, rank, PLO_SOLVER_LS, "plo_solve_ls"); }
 
 int plo_solve_wls_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, const double* w, int64_t n,
                        double delta[16], int32_t* rank) {
@@ -477,6 +497,7 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
   add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p);
   add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
+  add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);
   v.push_back((unsigned long long)c->n_levels);
   v.push_back((unsigned long long)c->n_raw_t);   // MapView.n_raw is a kernel argument
   v.push_back((unsigned long long)c->m_raw);     // launch geometry derives from it
@@ -516,6 +537,7 @@ static int build_loop_graph(plo_ctx* c) {
   const int64_t launches_before = c->launches;
   int rc = plo_launch_project(c, false);
   if (rc == PLO_OK) rc = plo_launch_reduce_solve(c, true, (unsigned long long)handle);
+  c->body_launches = (int)(c->launches - launches_before);   // kernels per loop iteration
   c->launches = launches_before;   // capture is not execution
   cudaGraph_t captured = nullptr;
   const cudaError_t e = cudaStreamEndCapture(c->stream, &captured);
@@ -530,7 +552,7 @@ static int build_loop_graph(plo_ctx* c) {
 
 static int enqueue_register(plo_ctx* c, const double* T0) {
   PLO_TRY(plo_reserve_query_buffers(c, false));
-  PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
+  PLO_TRY(plo_reserve_solver_buffers(c));
   PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
   if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
   PLO_TRY(plo_launch_init_state(c, T0));
@@ -579,7 +601,7 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
 static void count_graph_launches(plo_ctx* c, const DevState* s) {
   if (!c->graph_launched) return;
   const int bodies = s->iters + (s->status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0);
-  c->launches += 3 * (int64_t)bodies;
+  c->launches += (int64_t)c->body_launches * bodies;
   c->graph_launched = false;
 }
 
@@ -718,7 +740,7 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   if (!on_device && c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (rc == PLO_OK) {
     for (int i = 0; i < count; ++i) {
-      if (graph_units > 0) c->launches += 3 * (int64_t)(h_slots[i].iters + (h_slots[i].status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0));
+      if (graph_units > 0) c->launches += (int64_t)c->body_launches * (h_slots[i].iters + (h_slots[i].status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0));
       memcpy(T_out + 16 * (size_t)i, h_slots[i].rPose, sizeof(double) * 16);
       if (stats_out) fill_reg_stats(&h_slots[i], &stats_out[i], c->prm.iterations);
     }

@@ -52,6 +52,7 @@ struct DevState {
   double delta[16];
   double H[21];
   double g[6];
+  double x0[6];   // trimmed LS: solution of the untrimmed first pass (src/solver.cpp:107)
   double sw, swbb;
   double rms, delta_dist, delta_angle;
   long long pairs;
@@ -80,6 +81,8 @@ struct DevParams {
   int k, k_normal;
   int use_pca_normals, angle_constraint, transform_normal;
   int correspond_number, weight_mode, iterations;
+  int solver;            // plo_solver
+  double ls_threshold;   // LS.threshold (trim fraction at either end)
 };
 
 // ---------------------------------------------------------------------------------
@@ -130,6 +133,7 @@ struct plo_ctx {
 
   // reduction / solve
   DevBuf partials, state, counts, scratch, chunk_counter;
+  DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
   DevState* h_state = nullptr;       // pinned
   DevCounts* h_counts = nullptr;     // pinned
@@ -144,6 +148,7 @@ struct plo_ctx {
   // batched mode: host->device copies of pair i+1 overlap the registration of pair i
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_batch_start = nullptr;
+  int body_launches = 3;   // kernels per loop iteration of the captured body
   bool graph_launched = false;   // the last enqueue_register went through the graph
   bool graph_ok = true;      // cleared if the driver rejects conditional nodes: falls back to enqueue-all
   bool profiling = false;
@@ -173,12 +178,17 @@ static inline int plo_grid(const plo_ctx* c, int blocks_per_sm) { return c->sm_c
 // ---- index_build.cu ---------------------------------------------------------------
 int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
 int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
+int plo_sort_pairs(plo_ctx* c, unsigned long long* keys[2], int* vals[2], int64_t n, int passes, int* hist, int* digit_total,
+                   int* out_which);
+size_t plo_sort_hist_ints(int64_t n);
+size_t plo_sort_total_ints(int passes);
 // ---- knn_project.cu ---------------------------------------------------------------
 int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);
 int plo_reserve_query_buffers(plo_ctx* c, bool hooks);
 // ---- p2plane_solve.cu -------------------------------------------------------------
 int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long cond_handle = 0ull);
+int plo_reserve_solver_buffers(plo_ctx* c);
 int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const double* d_ref,
                                        const double* d_nrm, const double* d_w, int64_t n);
 int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null);

@@ -31,6 +31,6 @@ def solveMotionEstimationProblem(solve_method: str, in_cloud_vec, ref_cloud_vec,
                                  ctx: Context | None = None):
     """Dispatcher of src/laser_odometry.cpp:173-275 restricted to the in-scope method;
     unknown strings raise instead of printing (:271)."""
-    if solve_method in ("WeightedLS_CUDA", "Weighted LS", "LS_CUDA"):
+    if solve_method in ("WeightedLS_CUDA", "Weighted LS"):
         return SolveMotionEstimationProblemWeightedLS_CUDA(in_cloud_vec, ref_cloud_vec, ref_normal, None, timestamp, ctx)
     raise ValueError(f"Invalid SOLVE_METHOD! ({solve_method!r})")

@@ -550,3 +550,35 @@ def test_randomised_small_clouds_fuzz(oracle_mod):
         except AssertionError as e:
             raise AssertionError(f"trial {trial}: n_t={n_t} n_s={n_s} mode={mode} {kw}: {e}") from e
         ctx.close()
+
+
+def test_trimmed_ls_solver(oracle_mod):
+    """"next" row of SURVEY.md §8f, rank 2: SolveMotionEstimationProblemLS (src/solver.cpp:74-166) on the
+    device — first LS, |residual| rank window [thr*N, (1-thr)*N] by a stable radix sort, second LS."""
+    pair = W.hdl64_pair(max_source=30000)
+    ctx, orc = _both(oracle_mod, pair.target, pair.source, solver=1)
+    ctx.project(np.eye(4))
+    pr = ctx.pairs()
+    s, d, n = (pr[k].astype(np.float64) for k in ("src_xyz", "ref_xyz", "ref_n"))
+    for thr in (0.02, 0.1, 0.0):
+        ctx.set_params(plo.default_params(solver=1, ls_threshold=thr))
+        ctx.project(np.eye(4))
+        delta, rank = ctx.solve_ls()
+        Do = oracle_mod.solve_ls(s, d, n, thr)
+        assert rank == 6 and np.abs(delta - Do).max() < 1e-9, thr
+    # full loop, resident (CUDA graph) and stepped, against the oracle's LS loop
+    ctx, orc = _both(oracle_mod, pair.target, pair.source, solver=1)
+    Tg, sg = ctx.register()
+    To, so = orc.register()
+    assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    cfg = plo.config.load_config()
+    cfg["laser_odometry"]["solve_method"]["method"] = "LS"
+    odo = plo.LaserOdometry(cfg, resident=False)
+    odo.process_frame(pair.target)
+    _, st = odo.process_frame(pair.source)
+    assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
+    # and the weighted-LS result differs (the trim really changes the estimate)
+    ctx2, _ = _both(oracle_mod, pair.target, pair.source)
+    Tw, _ = ctx2.register()
+    assert np.abs(Tw - Tg).max() > 1e-7
