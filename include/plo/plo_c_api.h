@@ -69,9 +69,18 @@ typedef enum plo_reg_status {
 
 typedef enum plo_solver {
   PLO_SOLVER_WLS = 0, /* SolveMotionEstimationProblemWeightedLS, src/solver.cpp:168-220 (default)      */
-  PLO_SOLVER_LS = 1   /* SolveMotionEstimationProblemLS, src/solver.cpp:74-166: LS, then a second LS on  */
+  PLO_SOLVER_LS = 1,  /* SolveMotionEstimationProblemLS, src/solver.cpp:74-166: LS, then a second LS on  */
                       /* the pairs whose |residual| rank lies in [thr*N, (1-thr)*N] (2 % / 98 % trim)    */
+  PLO_SOLVER_RANSAC = 2 /* SolveMotionEstimationProblemRANSAC, src/solver.cpp:222-385 — the config.json   */
+                      /* default chain: FPS-3 hypotheses, inlier count, Huber/exp weights at the best     */
+                      /* hypothesis, then ransac_final (Weighted LS or DRPM, :499-603).  The reference's   */
+                      /* unseeded rand() (src/common.cpp:49) is replaced by xorshift64(ransac_seed).        */
 } plo_solver;
+
+typedef enum plo_ransac_final {
+  PLO_FINAL_WLS = 1,  /* "Weighted LS" */
+  PLO_FINAL_DRPM = 2  /* "DRPM" (config.json default) */
+} plo_ransac_final;
 
 typedef enum plo_weight_mode {
   PLO_W_UNIT = 0,     /* plain point-to-plane LS (weights = 1)                         */
@@ -101,6 +110,13 @@ typedef struct plo_params {
   double huber_threshold;          /* RANSAC.huber_threshold    (PLO_W_HUBER_EXP)  0.648 */
   int32_t solver;                  /* plo_solver                                       0 */
   double ls_threshold;             /* solve_method.LS.threshold (PLO_SOLVER_LS)     0.02 */
+  int32_t ransac_max_iterations;   /* RANSAC.max_iterations                         5000 */
+  double ransac_min_inliers_percentage; /* RANSAC.min_inliers_percentage            0.95 */
+  int32_t ransac_final;            /* plo_ransac_final (RANSAC.final_solve_method)  DRPM */
+  double drpm_threshold;           /* RANSAC.DRPM_threshold                         0.05 */
+  double drpm_stdev_points;        /* RANSAC.DRPM_stdev_points                      0.02 */
+  double drpm_stdev_normals;       /* RANSAC.DRPM_stdev_normals                     0.05 */
+  uint64_t ransac_seed;            /* seed of the hypothesis sampler (non-zero)        1 */
 } plo_params;
 
 typedef struct plo_proj_stats {
@@ -189,6 +205,11 @@ PLO_API int plo_solve_wls(plo_ctx* ctx, double delta[16], int32_t* rank);
  * device-resident pairs of the last plo_project, trim fraction = params.ls_threshold.  Ties in the
  * |residual| order are broken by pair index (std::sort there is unstable). */
 PLO_API int plo_solve_ls(plo_ctx* ctx, double delta[16], int32_t* rank);
+/* plo_solve_ransac == SolveMotionEstimationProblemRANSAC (src/solver.cpp:222-385) with the context's
+ * RANSAC / DRPM parameters on the device-resident pairs of the last plo_project.  probs[6] (nullable)
+ * receives DRPM's non-degeneracy probabilities (zeros for the Weighted-LS tail); inliers / hypotheses
+ * (nullable) the best hypothesis' inlier count and the number of hypotheses evaluated. */
+PLO_API int plo_solve_ransac(plo_ctx* ctx, double delta[16], double probs[6], int64_t* inliers, int32_t* hypotheses);
 /* same solver, reference-shaped inputs: host arrays of n x 3 doubles + n weights
  * (NULL = unit) — the argument list of SolveMotionEstimationProblemWeightedLS */
 PLO_API int plo_solve_wls_host(plo_ctx* ctx, const double* src, const double* ref,

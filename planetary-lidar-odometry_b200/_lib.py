@@ -18,7 +18,8 @@ ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "NO_DEVICE", -4: "UNSUPPORTED", -5:
 POINT_STATUS = ["ok", "no_normal", "too_far", "invalid_normal", "normal_constraint", "mls_fail", "nan_inf_height"]
 REG_STATUS = {1: "CONVERGED", 2: "MAX_ITERS", 3: "TOO_FEW_PAIRS", 4: "SOLVE_FAILED"}
 W_UNIT, W_HUBER_EXP = 0, 1
-SOLVER_WLS, SOLVER_LS = 0, 1
+SOLVER_WLS, SOLVER_LS, SOLVER_RANSAC = 0, 1, 2
+FINAL_WLS, FINAL_DRPM = 1, 2
 
 
 class PloError(RuntimeError):
@@ -36,6 +37,9 @@ class PloParams(C.Structure):
         ("delta_dist_threshold", C.c_double), ("delta_angle_threshold", C.c_double),
         ("weight_mode", C.c_int32), ("ransac_distance_threshold", C.c_double), ("huber_threshold", C.c_double),
         ("solver", C.c_int32), ("ls_threshold", C.c_double),
+        ("ransac_max_iterations", C.c_int32), ("ransac_min_inliers_percentage", C.c_double),
+        ("ransac_final", C.c_int32), ("drpm_threshold", C.c_double), ("drpm_stdev_points", C.c_double),
+        ("drpm_stdev_normals", C.c_double), ("ransac_seed", C.c_uint64),
     ]
 
 
@@ -53,7 +57,7 @@ EXPORTS = [
     "plo_create", "plo_destroy", "plo_last_error", "plo_version", "plo_set_stream", "plo_synchronize",
     "plo_default_params", "plo_set_params", "plo_set_target", "plo_set_source", "plo_set_target_device",
     "plo_set_source_device", "plo_target_size", "plo_source_size", "plo_project", "plo_get_pairs",
-    "plo_get_neighbors", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls", "plo_solve_ls",
+    "plo_get_neighbors", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls", "plo_solve_ls", "plo_solve_ransac",
     "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
     "plo_last_kernel_timings",
@@ -102,6 +106,7 @@ def lib() -> C.CDLL:
     L.plo_get_target_normals.argtypes = [vp, vp]
     L.plo_solve_wls.argtypes = [vp, vp, C.POINTER(i32)]
     L.plo_solve_ls.argtypes = [vp, vp, C.POINTER(i32)]
+    L.plo_solve_ransac.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(i32)]
     L.plo_solve_wls_host.argtypes = [vp, vp, vp, vp, vp, i64, vp, C.POINTER(i32)]
     L.plo_get_normal_equations.argtypes = [vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.plo_register.argtypes = [vp, vp, vp, C.POINTER(PloRegStats)]

@@ -12,9 +12,9 @@ Accepted selections
   solve_method.method    : "WeightedLS_CUDA" / "Weighted LS" (weighted LS, unit weights unless
                            "weights": "huber_exp"), "LS" / "LS_CUDA" (the reference's trimmed LS,
                            src/solver.cpp:74-166, threshold from solve_method.LS.threshold), or
-                           "RANSAC" with final_solve_method "Weighted LS" (mapped to the
-                           RANSAC-final Huber/exp weights evaluated at T_best = I)
-Everything else the reference lists (plane_ICP, Ceres, ICP, Teaser, RANSAC->DRPM/LS,
+                           "RANSAC" (the config.json default chain, src/solver.cpp:222-385) with
+                           final_solve_method "Weighted LS" or "DRPM" (src/solver.cpp:499-603)
+Everything else the reference lists (plane_ICP, Ceres, ICP, Teaser, RANSAC->LS,
 tensor voting, projected distance) is outside the hot-path scope and raises.
 """
 from __future__ import annotations
@@ -100,16 +100,21 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
     smethod = _get(sm, "method")
     weight_mode = _lib.W_UNIT
     solver = _lib.SOLVER_WLS
+    ransac_final = _lib.FINAL_DRPM
     if smethod in ("WeightedLS_CUDA", "Weighted LS"):
         weight_mode = _lib.W_HUBER_EXP if _get(sm, "weights", default="unit", required=False) == "huber_exp" else _lib.W_UNIT
     elif smethod in ("LS", "LS_CUDA"):
         solver = _lib.SOLVER_LS
     elif smethod == "RANSAC":
+        solver = _lib.SOLVER_RANSAC
         final = _get(sm, "RANSAC", "final_solve_method")
-        if final != "Weighted LS":
-            raise ConfigError(f'solve_method RANSAC -> "{final}" is a "next" row (SURVEY.md §8f); '
-                              'only final_solve_method "Weighted LS" maps onto the device solver')
-        weight_mode = _lib.W_HUBER_EXP
+        if final == "Weighted LS":
+            ransac_final = _lib.FINAL_WLS
+        elif final == "DRPM":
+            ransac_final = _lib.FINAL_DRPM
+        else:
+            raise ConfigError(f'solve_method RANSAC -> "{final}": only final_solve_method "Weighted LS" and "DRPM" '
+                              'run on the device')
     elif smethod in ("Ceres", "ICP", "Teaser"):
         raise ConfigError(f'solve_method "{smethod}" is outside the hot-path scope (SURVEY.md §2.1 row 2)')
     else:
@@ -133,4 +138,11 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
         huber_threshold=float(rs.get("huber_threshold", 0.648)),
         solver=solver,
         ls_threshold=float((_get(sm, "LS", default={}, required=False) or {}).get("threshold", 0.02)),
+        ransac_max_iterations=int(rs.get("max_iterations", 5000)),
+        ransac_min_inliers_percentage=float(rs.get("min_inliers_percentage", 0.95)),
+        ransac_final=ransac_final,
+        drpm_threshold=float(rs.get("DRPM_threshold", 0.05)),
+        drpm_stdev_points=float(rs.get("DRPM_stdev_points", 0.02)),
+        drpm_stdev_normals=float(rs.get("DRPM_stdev_normals", 0.05)),
+        ransac_seed=int(rs.get("seed", 1)),
     )

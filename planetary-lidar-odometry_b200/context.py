@@ -170,6 +170,14 @@ class Context:
         self._ck(self.L.plo_solve_ls(self.h, _ptr(d), C.byref(rank)))
         return d.reshape(4, 4), rank.value
 
+    def solve_ransac(self):
+        """SolveMotionEstimationProblemRANSAC (+ Weighted LS / DRPM tail) on the pairs of the last projection"""
+        d = np.empty(16, np.float64)
+        pr = np.zeros(6, np.float64)
+        inl, hyp = C.c_int64(), C.c_int32()
+        self._ck(self.L.plo_solve_ransac(self.h, _ptr(d), _ptr(pr), C.byref(inl), C.byref(hyp)))
+        return d.reshape(4, 4), dict(probs=pr, inliers=int(inl.value), hypotheses=int(hyp.value))
+
     def solve_wls_host(self, src, ref, nrm, w=None):
         src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
         w = None if w is None else np.ascontiguousarray(w, np.float64)

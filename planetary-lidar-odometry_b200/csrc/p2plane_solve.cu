@@ -38,10 +38,25 @@ __device__ __forceinline__ void ab_row(const double s[3], const double d[3], con
                 __dmul_rn(n[2], __dsub_rn(d[2], s[2])));
 }
 
-// RANSAC-final weight of src/solver.cpp:334-364 evaluated at T_best = I; < 0 => not an inlier
-__device__ __forceinline__ double huber_exp_weight(const double s[3], const double d[3], const double n[3], const DevParams& P) {
-  const double dist = fabs(__dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(s[0], d[0]), n[0]), __dmul_rn(__dsub_rn(s[1], d[1]), n[1])),
-                                     __dmul_rn(__dsub_rn(s[2], d[2]), n[2])));
+__device__ __forceinline__ void apply_T3(const double* __restrict__ T, const double s[3], double out[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    out[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[i * 4], s[0]), __dmul_rn(T[i * 4 + 1], s[1])), __dmul_rn(T[i * 4 + 2], s[2])), T[i * 4 + 3]);
+}
+
+// point-to-plane distance of a pair under hypothesis T (src/solver.cpp:306-307, :347-348)
+__device__ __forceinline__ double plane_distance(const double* __restrict__ T, const double s[3], const double d[3], const double n[3]) {
+  double tp[3];
+  apply_T3(T, s, tp);
+  return fabs(__dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(tp[0], d[0]), n[0]), __dmul_rn(__dsub_rn(tp[1], d[1]), n[1])),
+                        __dmul_rn(__dsub_rn(tp[2], d[2]), n[2])));
+}
+
+// RANSAC-final weight of src/solver.cpp:334-364 evaluated at hypothesis T (T_best of the RANSAC front,
+// or the identity for PLO_W_HUBER_EXP without RANSAC); < 0 => not an inlier
+__device__ __forceinline__ double huber_exp_weight(const double* __restrict__ T, const double s[3], const double d[3],
+                                                   const double n[3], const DevParams& P) {
+  const double dist = plane_distance(T, s, d, n);
   if (!(dist < P.ransac_dist_thr)) return -1.0;
   const double ar = exp(-dist);
   const double sq = sqrt(ar);
@@ -94,6 +109,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
 #pragma unroll
   for (int t = 0; t < PLO_NSUM; ++t) acc[t] = 0.0;
   const int n_src = counts->n_source;
+  double Tw[16];   // hypothesis the Huber/exp weights are evaluated at
+#pragma unroll
+  for (int t = 0; t < 16; ++t) Tw[t] = (P.solver == PLO_SOLVER_RANSAC) ? st->Tbest[t] : ((t % 5 == 0) ? 1.0 : 0.0);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
     const float4 x = __ldg(&qx[i]);
     const int status = __float_as_int(x.w);
@@ -108,7 +126,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
     if (mask != nullptr && mask[i] == 0) continue;   // trimmed LS, second pass: pair outside the kept rank window
     double w = 1.0;
     if (P.weight_mode == PLO_W_HUBER_EXP) {
-      w = huber_exp_weight(s, d, n, P);
+      w = huber_exp_weight(Tw, s, d, n, P);
       if (w < 0.0) continue;
     }
     accumulate_pair(acc, s, d, n, w);
@@ -170,7 +188,8 @@ __device__ void polar_orthogonalize(double R[9]) {
 // diagonally pivoted LDL^T solve of H x = g; returns the number of pivots used.
 // A pivot is dropped when the remaining diagonal is below (max|H_jj| * eps^2) * (cnt-k)/cnt,
 // the squared form of Eigen's ColPivHouseholderQR threshold_helper test (H_jj = |col j|^2).
-__device__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
+// (kept out of line: inlined into k_solve_update, nvcc 12.9 let the caller's x[] share a stack slot with A[][])
+__device__ __noinline__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
   double A[6][6];
   int t = 0;
   for (int p = 0; p < 6; ++p)
@@ -216,20 +235,187 @@ __device__ int solve_ldlt6(const double H21[21], const double g[6], double count
   return rank;
 }
 
-__global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
+// Eigen::ColPivHouseholderQR::solve for the 3 x 6 hypothesis system of src/solver.cpp:251-273 (basic
+// solution: three pivot columns solved, the other three unknowns zero) — same steps as Eigen 3.3's
+// computeInPlace / _solve_impl: largest remaining column norm first, LAPACK-style norm down-dating.
+__device__ __noinline__ void colpiv_qr_solve_3x6(double A[3][6], double b[3], double x[6]) {
+  const int m = 3, n = 6, size = 3;
+  double cnd[6], cnu[6], hcoef[3];
+  int perm[6];
+  double maxnorm = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double sacc = 0.0;
+    for (int i = 0; i < m; ++i) sacc += A[i][j] * A[i][j];
+    cnd[j] = cnu[j] = sqrt(sacc);
+    if (cnu[j] > maxnorm) maxnorm = cnu[j];
+    perm[j] = j;
+  }
+  const double eps = DBL_EPSILON;
+  const double threshold_helper = (maxnorm * eps) * (maxnorm * eps) / (double)m;
+  const double downdate_thr = sqrt(eps);
+  int nonzero_pivots = size;
+  for (int k = 0; k < size; ++k) {
+    int big = k;
+    double bigv = cnu[k];
+    for (int j = k + 1; j < n; ++j) if (cnu[j] > bigv) { bigv = cnu[j]; big = j; }
+    if (nonzero_pivots == size && bigv * bigv < threshold_helper * (double)(m - k)) nonzero_pivots = k;
+    if (big != k) {
+      for (int i = 0; i < m; ++i) { const double t = A[i][k]; A[i][k] = A[i][big]; A[i][big] = t; }
+      double t = cnu[k]; cnu[k] = cnu[big]; cnu[big] = t;
+      t = cnd[k]; cnd[k] = cnd[big]; cnd[big] = t;
+      const int ti = perm[k]; perm[k] = perm[big]; perm[big] = ti;
+    }
+    const double c0 = A[k][k];
+    double tail_sq = 0.0;
+    for (int i = k + 1; i < m; ++i) tail_sq += A[i][k] * A[i][k];
+    double tau, beta;
+    if (tail_sq <= DBL_MIN) {
+      tau = 0.0; beta = c0;
+      for (int i = k + 1; i < m; ++i) A[i][k] = 0.0;
+    } else {
+      beta = sqrt(c0 * c0 + tail_sq);
+      if (c0 >= 0.0) beta = -beta;
+      for (int i = k + 1; i < m; ++i) A[i][k] /= (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    hcoef[k] = tau;
+    A[k][k] = beta;
+    if (tau != 0.0) {
+      for (int j = k + 1; j < n; ++j) {
+        double sacc = A[k][j];
+        for (int i = k + 1; i < m; ++i) sacc += A[i][k] * A[i][j];
+        sacc *= tau;
+        A[k][j] -= sacc;
+        for (int i = k + 1; i < m; ++i) A[i][j] -= sacc * A[i][k];
+      }
+    }
+    for (int j = k + 1; j < n; ++j) {
+      if (cnu[j] != 0.0) {
+        double temp = fabs(A[k][j]) / cnu[j];
+        temp = (1.0 + temp) * (1.0 - temp);
+        if (temp < 0.0) temp = 0.0;
+        const double ratio = cnu[j] / cnd[j];
+        const double temp2 = temp * ratio * ratio;
+        if (temp2 <= downdate_thr) {
+          double sacc = 0.0;
+          for (int i = k + 1; i < m; ++i) sacc += A[i][j] * A[i][j];
+          cnd[j] = cnu[j] = sqrt(sacc);
+        } else {
+          cnu[j] *= sqrt(temp);
+        }
+      }
+    }
+  }
+  for (int j = 0; j < n; ++j) x[j] = 0.0;
+  if (nonzero_pivots == 0) return;
+  for (int k = 0; k < nonzero_pivots; ++k) {
+    const double tau = hcoef[k];
+    if (tau == 0.0) continue;
+    double sacc = b[k];
+    for (int i = k + 1; i < m; ++i) sacc += A[i][k] * b[i];
+    sacc *= tau;
+    b[k] -= sacc;
+    for (int i = k + 1; i < m; ++i) b[i] -= sacc * A[i][k];
+  }
+  double y[3];
+  for (int i = nonzero_pivots - 1; i >= 0; --i) {
+    double sacc = b[i];
+    for (int j = i + 1; j < nonzero_pivots; ++j) sacc -= A[i][j] * y[j];
+    y[i] = sacc / A[i][i];
+  }
+  for (int i = 0; i < nonzero_pivots; ++i) x[perm[i]] = y[i];
+}
+
+// cyclic Jacobi on a symmetric 6 x 6: eigenvalues ascending, eigenvectors in columns (the ordering
+// contract of Eigen::SelfAdjointEigenSolver, src/solver.cpp:540-542)
+__device__ __noinline__ void sym_eigen6(const double Ain[36], double ev[6], double U[36]) {
+  double A[36], V[36];
+  for (int i = 0; i < 36; ++i) { A[i] = Ain[i]; V[i] = (i % 7 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i + 1; j < 6; ++j) off += A[i * 6 + j] * A[i * 6 + j];
+    if (off == 0.0) break;
+    for (int pp = 0; pp < 6; ++pp)
+      for (int q = pp + 1; q < 6; ++q) {
+        const double apq = A[pp * 6 + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * 6 + q] - A[pp * 6 + pp]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < 6; ++k) { const double akp = A[k * 6 + pp], akq = A[k * 6 + q]; A[k * 6 + pp] = cs * akp - sn * akq; A[k * 6 + q] = sn * akp + cs * akq; }
+        for (int k = 0; k < 6; ++k) { const double apk = A[pp * 6 + k], aqk = A[q * 6 + k]; A[pp * 6 + k] = cs * apk - sn * aqk; A[q * 6 + k] = sn * apk + cs * aqk; }
+        for (int k = 0; k < 6; ++k) { const double vkp = V[k * 6 + pp], vkq = V[k * 6 + q]; V[k * 6 + pp] = cs * vkp - sn * vkq; V[k * 6 + q] = sn * vkp + cs * vkq; }
+      }
+  }
+  int order[6] = {0, 1, 2, 3, 4, 5};
+  for (int i = 0; i < 6; ++i)
+    for (int j = i + 1; j < 6; ++j)
+      if (A[order[j] * 7] < A[order[i] * 7]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+  for (int i = 0; i < 6; ++i) {
+    ev[i] = A[order[i] * 7];
+    for (int k = 0; k < 6; ++k) U[k * 6 + i] = V[k * 6 + order[i]];
+  }
+}
+
+// x -> deltaTrans (src/solver.cpp:203-217): Rodrigues, orthogonal polar factor, translation
+__device__ void delta_from_x(const double x[6], double D[16]) {
+  double R[9];
+  rodrigues(x, R);
+  polar_orthogonalize(R);
+  const double Dl[16] = {R[0], R[1], R[2], x[3], R[3], R[4], R[5], x[4], R[6], R[7], R[8], x[5], 0.0, 0.0, 0.0, 1.0};
+  for (int i = 0; i < 16; ++i) D[i] = Dl[i];
+}
+
+// tail of one loop iteration (one thread): delta, rPose = delta * rPose (src/laser_odometry.cpp:619),
+// convergence test (:628-646), loop condition of the resident graph
+__device__ void finish_iteration(DevState* __restrict__ st, const DevParams& P, const double x[6], int rank, int advance_loop,
+                                 cudaGraphConditionalHandle cond, int use_cond) {
+  st->rank = rank;
+  double D[16];
+  delta_from_x(x, D);
+  for (int i = 0; i < 16; ++i) st->delta[i] = D[i];
+  const double dd = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);   // :628-632
+  double ct = ((D[0] + D[5] + D[10]) - 1.0) / 2.0;                   // :636-638
+  ct = fmin(1.0, fmax(ct, -1.0));
+  const double da = acos(ct);
+  st->delta_dist = dd;
+  st->delta_angle = da;
+  if (!advance_loop) return;
+  double nP[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double sacc = 0.0;
+      for (int k = 0; k < 4; ++k) sacc += D[i * 4 + k] * st->rPose[k * 4 + j];
+      nP[i * 4 + j] = sacc;
+    }
+  for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
+  st->iters += 1;
+  st->use_prev = 1;   // the projection just consumed left its k-th distances behind
+  // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
+  // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
+  st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
+  if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
+  else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
+  if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
+}
+
+__global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
                                                        DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond,
                                                        int stage) {
   // stage 0: weighted LS (one pass).  Trimmed LS (src/solver.cpp:74-166): stage 1 = first solve on all pairs,
   // only x0 is kept (:107); stage 2 = second solve on the pairs selected by residual rank (:137) + loop tail.
+  // DRPM (src/solver.cpp:499-603): stage 3 = eigen-decomposition of the weighted information matrix; the
+  // noise estimate and the solve follow in k_drpm_noise / k_drpm_finish.
   if (advance_loop && st->done) {
     if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
     return;
   }
   __shared__ double s_sum[PLO_NSUM];
   {
-    // value t is summed by warp (t mod 32): lane-strided partial sums in a fixed order, fixed shuffle tree
+    // value t is summed by warp (t mod 8): lane-strided partial sums in a fixed order, fixed shuffle tree
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = warp; t < PLO_NSUM; t += 32) {
+    for (int t = warp; t < PLO_NSUM; t += 8) {
       double v = 0.0;
       for (int b = lane; b < n_partials; b += 32) v += partials[(size_t)b * PLO_NSUM + t];
 #pragma unroll
@@ -261,41 +447,331 @@ __global__ void __launch_bounds__(1024) k_solve_update(const double* __restrict_
   const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
   for (int i = 0; i < 21; ++i) H[i] = s_sum[i] * scale;
   for (int i = 0; i < 6; ++i) g[i] = s_sum[21 + i] * scale;
+  if (stage == 3) {   // DRPM: eigenvectors of the normalised information matrix (src/solver.cpp:537-542)
+    double Hf[36];
+    int t = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) { Hf[a * 6 + b] = H[t]; Hf[b * 6 + a] = H[t]; ++t; }
+    double ev[6], U[36];
+    sym_eigen6(Hf, ev, U);
+    for (int i = 0; i < 36; ++i) st->U[i] = U[i];
+    for (int i = 0; i < 6; ++i) st->ev[i] = ev[i];
+    return;
+  }
   double x[6];
   const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
-  st->rank = rank;
   if (stage == 1) {
+    st->rank = rank;
     for (int i = 0; i < 6; ++i) st->x0[i] = x[i];
     return;   // the loop condition keeps its value (1): the body goes on with the selection
   }
-  double R[9];
-  rodrigues(x, R);
-  polar_orthogonalize(R);
-  double D[16] = {R[0], R[1], R[2], x[3], R[3], R[4], R[5], x[4], R[6], R[7], R[8], x[5], 0.0, 0.0, 0.0, 1.0};
-  for (int i = 0; i < 16; ++i) st->delta[i] = D[i];
-  const double dd = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);   // :628-632
-  double ct = ((R[0] + R[4] + R[8]) - 1.0) / 2.0;                    // :636-638
-  ct = fmin(1.0, fmax(ct, -1.0));
-  const double da = acos(ct);
-  st->delta_dist = dd;
-  st->delta_angle = da;
-  if (!advance_loop) return;
-  double nP[16];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      double sacc = 0.0;
-      for (int k = 0; k < 4; ++k) sacc += D[i * 4 + k] * st->rPose[k * 4 + j];
-      nP[i * 4 + j] = sacc;
+  for (int i = 0; i < 6; ++i) st->probs[i] = 0.0;
+  finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
+}
+
+// ---- RANSAC front (src/solver.cpp:238-326) on the compacted pairs, one block --------------------
+
+__device__ __forceinline__ unsigned long long xorshift64(unsigned long long x) {
+  x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+  return x;
+}
+
+// block-wide argmax of (value, index): larger value wins, ties go to the smaller index; index -1 = none
+__device__ __forceinline__ void block_argmax(double v, int idx, double* s_val, int* s_idx, int* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(PLO_FULL_MASK, v, o);
+    const int oi = __shfl_xor_sync(PLO_FULL_MASK, idx, o);
+    if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+  }
+  if (lane == 0) { s_val[warp] = v; s_idx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    v = s_val[lane]; idx = s_idx[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(PLO_FULL_MASK, v, o);
+      const int oi = __shfl_xor_sync(PLO_FULL_MASK, idx, o);
+      if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
     }
-  for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
-  st->iters += 1;
-  st->use_prev = 1;   // the projection just consumed left its k-th distances behind
-  // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
-  // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
-  st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
-  if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
-  else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
-  if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
+    if (lane == 0) *out = idx;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load3(const float* __restrict__ a, int i, double out[3]) {
+  out[0] = (double)a[3 * (size_t)i]; out[1] = (double)a[3 * (size_t)i + 1]; out[2] = (double)a[3 * (size_t)i + 2];
+}
+
+__device__ __forceinline__ double dist3(const double a[3], const double b[3]) {
+  const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+__global__ void __launch_bounds__(1024) k_ransac(const float* __restrict__ src, const float* __restrict__ ref,
+                                                 const float* __restrict__ nrm, const DevCounts* __restrict__ counts,
+                                                 DevState* __restrict__ st, DevParams P, double* __restrict__ mind, int respect_done) {
+  if (respect_done && st->done) return;
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ long long s_cnt[32];
+  __shared__ double s_T[16];
+  __shared__ int s_sel[3];
+  __shared__ int s_stop;
+  const int n = counts->n_pairs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long rng = P.ransac_seed;
+  long long best = 0;
+  double Tbest[16];
+  for (int i = 0; i < 16; ++i) Tbest[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  int iters = 0;
+  if (n > 0) {
+    const int min_inliers = (int)(P.ransac_min_inliers_pct * (double)n);   // :238
+    for (int it = 0; it < P.ransac_max_iterations; ++it) {   // :244
+      // ---- farthestPointSampling(source_cloud, 3), src/common.cpp:19-82 ----
+      if (tid == 0) {
+        rng = xorshift64(rng);
+        s_sel[0] = (int)(rng % (unsigned long long)n);
+        s_stop = 0;
+      }
+      __syncthreads();
+      const int first = s_sel[0];
+      double pf[3];
+      load3(src, first, pf);
+      double bv = -1.0;
+      int bi = -1;
+      for (int i = tid; i < n; i += 1024) {
+        double pi[3];
+        load3(src, i, pi);
+        const double d = dist3(pf, pi);
+        mind[i] = d;
+        if (i != first && d > bv) { bv = d; bi = i; }
+      }
+      block_argmax(bv, bi, s_val, s_idx, &s_sel[1]);
+      int second = s_sel[1];
+      const bool have_second = second >= 0;
+      if (!have_second) second = first;
+      double ps[3];
+      load3(src, second, ps);
+      bv = -1.0;
+      bi = -1;
+      for (int i = tid; i < n; i += 1024) {
+        double m = mind[i];
+        if (have_second) {
+          double pi[3];
+          load3(src, i, pi);
+          const double d = dist3(ps, pi);
+          if (d < m) { m = d; mind[i] = m; }
+        }
+        if (i != first && i != second && m > bv) { bv = m; bi = i; }
+      }
+      block_argmax(bv, bi, s_val, s_idx, &s_sel[2]);
+      if (tid == 0) {
+        int ids[3] = {first, second, s_sel[2] >= 0 ? s_sel[2] : first};
+        double A[3][6], b[3], x[6];
+        for (int r = 0; r < 3; ++r) {   // :255-270
+          double sv[3], dv[3], nv[3];
+          load3(src, ids[r], sv); load3(ref, ids[r], dv); load3(nrm, ids[r], nv);
+          ab_row(sv, dv, nv, A[r], b[r]);
+        }
+        colpiv_qr_solve_3x6(A, b, x);   // :273
+        double D[16];
+        delta_from_x(x, D);             // :276-298
+        for (int i = 0; i < 16; ++i) s_T[i] = D[i];
+      }
+      __syncthreads();
+      // ---- inlier count, :300-314 ----
+      double T[16];
+      for (int i = 0; i < 16; ++i) T[i] = s_T[i];
+      long long cnt = 0;
+      for (int i = tid; i < n; i += 1024) {
+        double sv[3], dv[3], nv[3];
+        load3(src, i, sv); load3(ref, i, dv); load3(nrm, i, nv);
+        cnt += (plane_distance(T, sv, dv, nv) < P.ransac_dist_thr) ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(PLO_FULL_MASK, cnt, o);
+      if (lane == 0) s_cnt[warp] = cnt;
+      __syncthreads();
+      if (tid == 0) {
+        long long total = 0;
+        for (int w = 0; w < 32; ++w) total += s_cnt[w];
+        if (total > best) { best = total; for (int i = 0; i < 16; ++i) Tbest[i] = s_T[i]; }   // :317-320
+        if (best > (long long)min_inliers) s_stop = 1;                                       // :323-325
+      }
+      iters = it + 1;
+      __syncthreads();
+      if (s_stop) break;
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 16; ++i) st->Tbest[i] = Tbest[i];
+    st->ransac_best = best;
+    st->ransac_iters = iters;
+  }
+}
+
+// ---- DRPM noise estimate: degeneracy::ComputeNoiseEstimate, include/degeneracy.h:14-72 ----------
+constexpr int kNoiseSums = 42;   // 36 mean + 6 variance
+
+__global__ void __launch_bounds__(kReduceThreads) k_drpm_noise(const float4* __restrict__ qx, const float4* __restrict__ qy,
+                                                               const float4* __restrict__ qn,
+                                                               const DevCounts* __restrict__ counts,
+                                                               const DevState* __restrict__ st, DevParams P,
+                                                               double* __restrict__ partials2, int respect_done) {
+  if (respect_done && st->done) return;
+  __shared__ double s_U[36];
+  __shared__ double s_T[16];
+  __shared__ double s_red[kReduceThreads / 32][kNoiseSums];
+  if (threadIdx.x < 36) s_U[threadIdx.x] = st->U[threadIdx.x];
+  if (threadIdx.x < 16) s_T[threadIdx.x] = st->Tbest[threadIdx.x];
+  __syncthreads();
+  const double inv_sw = st->sw > 0.0 ? 1.0 / st->sw : 0.0;
+  double acc[kNoiseSums];
+#pragma unroll
+  for (int t = 0; t < kNoiseSums; ++t) acc[t] = 0.0;
+  const int n_src = counts->n_source;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+    const float4 x = __ldg(&qx[i]);
+    if (__float_as_int(x.w) != PLO_PT_OK) continue;
+    const float4 y = __ldg(&qy[i]);
+    const float4 nn = __ldg(&qn[i]);
+    const double p[3] = {(double)x.x, (double)x.y, (double)x.z};
+    const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
+    const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
+    double w = huber_exp_weight(s_T, p, d, n, P);
+    if (w < 0.0) continue;
+    w *= inv_sw;   // weights normalised to sum 1 (src/solver.cpp:361-364)
+    // B = [[-nx, px*nx], [0, nx]] (6x6), Ncov = diag(sp2 I3, sn2 I3)   (:39-51)
+    const double nx[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
+    const double px[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+    double B[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) B[r][c] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sacc += px[r * 3 + k] * nx[k * 3 + c];
+        B[r][c] = -nx[r * 3 + c];
+        B[r][3 + c] = sacc;
+        B[3 + r][3 + c] = nx[r * 3 + c];
+      }
+    const double sq = sqrt(w);
+    const double v[6] = {sq * (px[0] * n[0] + px[1] * n[1] + px[2] * n[2]), sq * (px[3] * n[0] + px[4] * n[1] + px[5] * n[2]),
+                         sq * (px[6] * n[0] + px[7] * n[1] + px[8] * n[2]), sq * n[0], sq * n[1], sq * n[2]};   // :58-60
+    double a[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double Crow[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sacc += B[r][k] * (k < 3 ? P.drpm_sp2 : P.drpm_sn2) * B[c][k];
+        Crow[c] = sacc * w;   // :53
+        acc[r * 6 + c] += Crow[c];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {   // a_k = u_k^T C u_k, accumulated row by row
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) t += Crow[c] * s_U[c * 6 + k];
+        a[k] += s_U[r * 6 + k] * t;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {   // :63-69
+      double bb = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) bb += s_U[r * 6 + k] * v[r];
+      acc[36 + k] += 2.0 * a[k] * a[k] + 4.0 * a[k] * bb * bb;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < kNoiseSums; ++t) {
+    double vv = acc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(PLO_FULL_MASK, vv, o);
+    if (lane == 0) s_red[warp][t] = vv;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNoiseSums) {
+    double vv = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < kReduceThreads / 32; ++w2) vv += s_red[w2][threadIdx.x];
+    partials2[(size_t)blockIdx.x * kNoiseSums + threadIdx.x] = vv;
+  }
+}
+
+// probabilities (degeneracy::ComputeSignalToNoiseProbabilities, include/degeneracy.h:74-105), the
+// probability-weighted pseudo-inverse (:107-131) or the plain weighted solve, then the loop tail
+__global__ void __launch_bounds__(64) k_drpm_finish(const double* __restrict__ partials2, int n_partials, DevState* __restrict__ st,
+                                                    DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond) {
+  if (advance_loop && st->done) {
+    if (use_cond && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
+    return;
+  }
+  __shared__ double s_sum[kNoiseSums];
+  if (threadIdx.x < kNoiseSums) {
+    double v = 0.0;
+    for (int b = 0; b < n_partials; ++b) v += partials2[(size_t)b * kNoiseSums + threadIdx.x];   // fixed order
+    s_sum[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double sw = st->sw;
+  const double scale = sw > 0.0 ? 1.0 / sw : 1.0;
+  double H[21], g[6], Hf[36];
+  for (int i = 0; i < 21; ++i) H[i] = st->H[i] * scale;
+  for (int i = 0; i < 6; ++i) g[i] = st->g[i] * scale;
+  int t = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int b = a; b < 6; ++b) { Hf[a * 6 + b] = H[t]; Hf[b * 6 + a] = H[t]; ++t; }
+  double probs[6], minp = CUDART_INF;
+  for (int k = 0; k < 6; ++k) {
+    double meas = 0.0, noise = 0.0;
+    for (int r = 0; r < 6; ++r) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int c = 0; c < 6; ++c) { t1 += Hf[r * 6 + c] * st->U[c * 6 + k]; t2 += s_sum[r * 6 + c] * st->U[c * 6 + k]; }
+      meas += st->U[r * 6 + k] * t1;
+      noise += st->U[r * 6 + k] * t2;
+    }
+    const double sd = sqrt(s_sum[36 + k]);
+    const double test_point = meas / (1.0 + 10.0);   // snr_factor = 10, src/solver.cpp:547
+    double pr;
+    if (!(noise == noise) || !(sd == sd) || !(test_point == test_point)) pr = 0.0;
+    else if (!(sd > 0.0)) pr = test_point >= noise ? 1.0 : 0.0;
+    else pr = 0.5 * erfc(-(test_point - noise) / (sd * sqrt(2.0)));   // boost normal cdf
+    probs[k] = pr;
+    st->probs[k] = pr;
+    if (pr < minp) minp = pr;
+  }
+  double x[6];
+  int rank = 6;
+  if (minp < P.drpm_threshold) {   // SolveWithSnrProbabilities, include/degeneracy.h:107-131
+    double tt[6];
+    for (int i = 0; i < 6; ++i) {
+      double sacc = 0.0;
+      for (int r = 0; r < 6; ++r) sacc += st->U[r * 6 + i] * g[r];
+      const double dps = fabs(st->ev[i]) > 1e-10 ? probs[i] / st->ev[i] : 0.0;
+      tt[i] = sacc * dps;
+    }
+    for (int r = 0; r < 6; ++r) {
+      double sacc = 0.0;
+      for (int i = 0; i < 6; ++i) sacc += st->U[r * 6 + i] * tt[i];
+      x[r] = sacc;
+    }
+  } else {
+    rank = solve_ldlt6(H, g, (double)st->pairs, x);   // weighted_A.colPivHouseholderQr().solve(weighted_b), :576
+  }
+  finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
 }
 
 // trimmed LS: |A_i x0 - b_i| of every surviving pair as a sortable 64-bit key (src/solver.cpp:110-122);
@@ -352,7 +828,12 @@ __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
       st->delta[i] = id;
     }
     for (int i = 0; i < 21; ++i) st->H[i] = 0.0;
-    for (int i = 0; i < 6; ++i) { st->g[i] = 0.0; st->dropped[i] = 0; st->x0[i] = 0.0; }
+    for (int i = 0; i < 6; ++i) { st->g[i] = 0.0; st->dropped[i] = 0; st->x0[i] = 0.0; st->ev[i] = 0.0; st->probs[i] = 0.0; }
+    for (int i = 0; i < 16; ++i) st->Tbest[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 36; ++i) st->U[i] = 0.0;
+    st->ransac_best = 0;
+    st->ransac_iters = 0;
+    st->pad0 = 0;
     st->sw = st->swbb = st->rms = st->delta_dist = st->delta_angle = 0.0;
     st->pairs = 0;
     st->iters = 0;
@@ -452,6 +933,16 @@ int plo_reserve_solver_buffers(plo_ctx* c) {
     PLO_CUDA(c, c->ls_tot.reserve(sizeof(int) * plo_sort_total_ints(kLsPasses)));
     PLO_CUDA(c, c->ls_mask.reserve(sizeof(int) * m));
   }
+  if (c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0) {
+    const size_t m = (size_t)c->m_raw;
+    PLO_CUDA(c, c->h_src.reserve(sizeof(double) * 3 * m));   // also sized for plo_solve_wls_host
+    PLO_CUDA(c, c->h_ref.reserve(sizeof(double) * 3 * m));
+    PLO_CUDA(c, c->h_nrm.reserve(sizeof(double) * 3 * m));
+    PLO_CUDA(c, c->h_w.reserve(sizeof(double) * m));
+    PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * ((m + kTile - 1) / kTile + 1)));
+    PLO_CUDA(c, c->ransac_mind.reserve(sizeof(double) * m));
+    PLO_CUDA(c, c->partials2.reserve(sizeof(double) * kNoiseSums * (size_t)plo_grid(c, 2)));
+  }
   return PLO_OK;
 }
 
@@ -462,8 +953,19 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   const cudaGraphConditionalHandle cond = (cudaGraphConditionalHandle)cond_handle;
   const int use_cond = cond_handle ? 1 : 0;
   const bool trimmed = c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0;
+  const bool ransac = c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0;
   DevParams P = c->dprm;
-  if (trimmed) P.weight_mode = PLO_W_UNIT;   // SolveMotionEstimationProblemLS is unweighted
+  if (trimmed) P.weight_mode = PLO_W_UNIT;       // SolveMotionEstimationProblemLS is unweighted
+  if (ransac) P.weight_mode = PLO_W_HUBER_EXP;   // Huber/exp weights at the best hypothesis (src/solver.cpp:334-364)
+  if (c->dprm.solver == PLO_SOLVER_RANSAC && !ransac) P.solver = PLO_SOLVER_WLS;   // empty source: nothing to sample
+  if (ransac) {
+    // the hypothesis sampler works on the compacted pair list (indices = positions in source_cloud)
+    PLO_TRY(plo_launch_compact_pairs(c, c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->h_w.as<int32_t>()));
+    k_ransac<<<1, 1024, 0, c->stream>>>(c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->counts.as<DevCounts>(),
+                                        c->state.as<DevState>(), P, c->ransac_mind.as<double>(), adv);
+    c->launches++;
+    PLO_CUDA(c, cudaGetLastError());
+  }
   if (c->m_raw > 0) {
     k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                         c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
@@ -471,10 +973,22 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
   }
-  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), P, adv, cond,
-                                            use_cond, trimmed ? 1 : 0);
+  const bool drpm = ransac && c->dprm.ransac_final == PLO_FINAL_DRPM;
+  k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), P, adv, cond,
+                                            use_cond, trimmed ? 1 : (drpm ? 3 : 0));
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
+  if (drpm) {
+    k_drpm_noise<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
+                                                      c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
+                                                      c->partials2.as<double>(), adv);
+    c->launches++;
+    PLO_CUDA(c, cudaGetLastError());
+    k_drpm_finish<<<1, 64, 0, c->stream>>>(c->partials2.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond);
+    c->launches++;
+    PLO_CUDA(c, cudaGetLastError());
+    return PLO_OK;
+  }
   if (!trimmed) return PLO_OK;
   // ---- trimmed LS: residual keys -> stable sort -> rank window -> second reduce + solve ----
   const int m = (int)c->m_raw;
@@ -496,7 +1010,7 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
                                                       c->partials.as<double>(), adv, c->ls_mask.as<int>());
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
-  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond, 2);
+  k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond, 2);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
@@ -513,7 +1027,7 @@ int plo_launch_reduce_solve_host_pairs(plo_ctx* c, const double* d_src, const do
   }
   DevParams P = c->dprm;
   P.weight_mode = PLO_W_UNIT;   // caller-supplied weights are used as they are
-  k_solve_update<<<1, 1024, 0, c->stream>>>(c->partials.as<double>(), n > 0 ? g : 0, c->state.as<DevState>(), P, 0,
+  k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), n > 0 ? g : 0, c->state.as<DevState>(), P, 0,
                                             (cudaGraphConditionalHandle)0, 0, 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());

@@ -83,6 +83,13 @@ static void flatten_params(plo_ctx* c) {
   d.iterations = p.iterations;
   d.solver = p.solver;
   d.ls_threshold = p.ls_threshold;
+  d.ransac_max_iterations = p.ransac_max_iterations;
+  d.ransac_final = p.ransac_final;
+  d.ransac_min_inliers_pct = p.ransac_min_inliers_percentage;
+  d.drpm_threshold = p.drpm_threshold;
+  d.drpm_sp2 = p.drpm_stdev_points * p.drpm_stdev_points;     // include/degeneracy.h:49
+  d.drpm_sn2 = p.drpm_stdev_normals * p.drpm_stdev_normals;   // src/solver.cpp:486-497
+  d.ransac_seed = p.ransac_seed ? p.ransac_seed : 1ull;
 }
 
 extern "C" {
@@ -110,6 +117,13 @@ void plo_default_params(plo_params* p) {
   p->huber_threshold = 0.648;              // :148
   p->solver = PLO_SOLVER_WLS;
   p->ls_threshold = 0.02;                  // :141
+  p->ransac_max_iterations = 5000;         // :145
+  p->ransac_min_inliers_percentage = 0.95; // :147
+  p->ransac_final = PLO_FINAL_DRPM;        // :149
+  p->drpm_threshold = 0.05;                // :151
+  p->drpm_stdev_points = 0.02;             // :152
+  p->drpm_stdev_normals = 0.05;            // :153
+  p->ransac_seed = 1;
 }
 
 int plo_create(int device, plo_ctx** out) {
@@ -167,7 +181,7 @@ void plo_destroy(plo_ctx* c) {
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
                     &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
-                    &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
+                    &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
   if (c->h_state) cudaFreeHost(c->h_state);
@@ -213,8 +227,10 @@ int plo_set_params(plo_ctx* c, const plo_params* p) {
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: h, r, r_normal must be >= 0");
   if (p->weight_mode != PLO_W_UNIT && p->weight_mode != PLO_W_HUBER_EXP)
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown weight_mode");
-  if (p->solver != PLO_SOLVER_WLS && p->solver != PLO_SOLVER_LS)
+  if (p->solver != PLO_SOLVER_WLS && p->solver != PLO_SOLVER_LS && p->solver != PLO_SOLVER_RANSAC)
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown solver");
+  if (p->solver == PLO_SOLVER_RANSAC && p->ransac_final != PLO_FINAL_WLS && p->ransac_final != PLO_FINAL_DRPM)
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_set_params: RANSAC final_solve_method must be Weighted LS or DRPM");
   if (p->solver == PLO_SOLVER_LS && !(p->ls_threshold >= 0.0 && p->ls_threshold < 0.5))
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: ls_threshold must be in [0, 0.5)");
   const bool pca_changed = c->prm.r_normal != p->r_normal || c->prm.search_number_normal != p->search_number_normal ||
@@ -452,6 +468,14 @@ int plo_solve_wls(plo_ctx* c, double delta[16], int32_t* rank) { return solve_on
 
 int plo_solve_ls(plo_ctx* c, double delta[16], int32_t* rank) { return solve_on_pairs(c, delta, rank, PLO_SOLVER_LS, "plo_solve_ls"); }
 
+int plo_solve_ransac(plo_ctx* c, double delta[16], double probs[6], int64_t* inliers, int32_t* hypotheses) {
+  PLO_TRY(solve_on_pairs(c, delta, nullptr, PLO_SOLVER_RANSAC, "plo_solve_ransac"));
+  if (probs) memcpy(probs, c->h_state->probs, sizeof(double) * 6);
+  if (inliers) *inliers = c->h_state->ransac_best;
+  if (hypotheses) *hypotheses = c->h_state->ransac_iters;
+  return PLO_OK;
+}
+
 int plo_solve_wls_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, const double* w, int64_t n,
                        double delta[16], int32_t* rank) {
   if (!c || !delta || n < 0 || (n > 0 && (!src || !ref || !nrm)))
@@ -498,6 +522,7 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p);
   add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
   add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);
+  add(c->ransac_mind.p); add(c->partials2.p); add(c->h_src.p); add(c->h_ref.p); add(c->h_nrm.p); add(c->h_w.p); add(c->blockcnt.p);
   v.push_back((unsigned long long)c->n_levels);
   v.push_back((unsigned long long)c->n_raw_t);   // MapView.n_raw is a kernel argument
   v.push_back((unsigned long long)c->m_raw);     // launch geometry derives from it

@@ -53,6 +53,13 @@ struct DevState {
   double H[21];
   double g[6];
   double x0[6];   // trimmed LS: solution of the untrimmed first pass (src/solver.cpp:107)
+  double Tbest[16];   // RANSAC: best hypothesis (src/solver.cpp:317-320), identity otherwise
+  double U[36];       // DRPM: eigenvectors of the weighted information matrix (columns), ascending eigenvalues
+  double ev[6];
+  double probs[6];    // DRPM: non-degeneracy probabilities (include/degeneracy.h:74-105)
+  long long ransac_best;   // inliers of the best hypothesis
+  int ransac_iters;        // hypotheses evaluated
+  int pad0;
   double sw, swbb;
   double rms, delta_dist, delta_angle;
   long long pairs;
@@ -83,6 +90,10 @@ struct DevParams {
   int correspond_number, weight_mode, iterations;
   int solver;            // plo_solver
   double ls_threshold;   // LS.threshold (trim fraction at either end)
+  int ransac_max_iterations, ransac_final;
+  double ransac_min_inliers_pct;
+  double drpm_threshold, drpm_sp2, drpm_sn2;
+  unsigned long long ransac_seed;
 };
 
 // ---------------------------------------------------------------------------------
@@ -134,6 +145,7 @@ struct plo_ctx {
   // reduction / solve
   DevBuf partials, state, counts, scratch, chunk_counter;
   DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
+  DevBuf ransac_mind, partials2;                              // RANSAC FPS distances, DRPM noise partials
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
   DevState* h_state = nullptr;       // pinned
   DevCounts* h_counts = nullptr;     // pinned

@@ -57,7 +57,10 @@ class LaserOdometry:
             if pairs < p.correspond_number:            # :570-576
                 status = 3
                 break
-            delta, _rank = self.ctx.solve_ls() if p.solver == 1 else self.ctx.solve_wls()   # :609 on the device-resident pairs
+            if p.solver == 2:                          # :609 on the device-resident pairs
+                delta = self.ctx.solve_ransac()[0]
+            else:
+                delta, _rank = self.ctx.solve_ls() if p.solver == 1 else self.ctx.solve_wls()
             rPose = delta @ rPose                      # :619
             iters += 1
             dd = float(np.sqrt(delta[0, 3] ** 2 + delta[1, 3] ** 2 + delta[2, 3] ** 2))

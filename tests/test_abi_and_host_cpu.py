@@ -74,13 +74,18 @@ def test_config_flattening_and_rejections(tmp_path):
     f = tmp_path / "config.json"
     f.write_text(json.dumps(ref_like))
     p = plo.config.params_from_config(plo.config.load_config(str(f)))
-    assert p.weight_mode == 1
+    assert p.solver == 2 and p.ransac_final == 1
+    # the reference's literal default chain: RANSAC -> DRPM
+    ref_default = json.loads(json.dumps(ref_like))
+    ref_default["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "DRPM"
+    p = plo.config.params_from_config(ref_default)
+    assert p.solver == 2 and p.ransac_final == 2 and p.drpm_threshold == 0.05
     for mutate, msg in [
         (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "plane_ICP"), "plane_ICP"),
         (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "bogus"), "Invalid MATCHING_METHOD"),
         (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "Teaser"), "Teaser"),
         (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "nope"), "Invalid SOLVE_METHOD"),
-        (lambda c: c["laser_odometry"]["solve_method"]["RANSAC"].__setitem__("final_solve_method", "DRPM"), "DRPM"),
+        (lambda c: c["laser_odometry"]["solve_method"]["RANSAC"].__setitem__("final_solve_method", "LS"), "only final_solve_method"),
         (lambda c: c["laser_odometry"]["matching_method"]["IMLS"]["use_tensor_voting"].__setitem__("enabled", True), "tensor"),
         (lambda c: c.__setitem__("backend", "cpu"), "no CPU fallback"),
     ]:

@@ -582,3 +582,46 @@ def test_trimmed_ls_solver(oracle_mod):
     ctx2, _ = _both(oracle_mod, pair.target, pair.source)
     Tw, _ = ctx2.register()
     assert np.abs(Tw - Tg).max() > 1e-7
+
+
+@pytest.mark.parametrize("final", [1, 2])
+def test_ransac_front_and_drpm_tail(oracle_mod, final):
+    """"next" row of SURVEY.md §8f, rank 1 — the literal config.json default chain on the device:
+    RANSAC (FPS-3 hypotheses seeded by xorshift64 instead of the reference's rand(), inlier count,
+    Huber/exp weights at the best hypothesis) then Weighted LS (final=1) or DRPM (final=2)."""
+    pair = W.hdl64_pair(max_source=20000)
+    kw = dict(solver=2, ransac_final=final)
+    ctx, orc = _both(oracle_mod, pair.target, pair.source, **kw)
+    ctx.project(np.eye(4))
+    pr = ctx.pairs()
+    s, d, n = (pr[k].astype(np.float64) for k in ("src_xyz", "ref_xyz", "ref_n"))
+    delta, info = ctx.solve_ransac()
+    ok, Do = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(**kw))
+    assert ok and np.abs(delta - Do).max() < 1e-9
+    assert 1 <= info["hypotheses"] <= 5000 and info["inliers"] > 0.95 * pr["n"]
+    if final == 2:
+        # probabilities against the oracle's DRPM on the same inliers / weights
+        idx, w = oracle_mod.ransac_weights(s, d, n)       # T_best differs, but with > 95 % inliers the sets coincide here
+        assert (info["probs"] >= 0).all() and (info["probs"] <= 1).all()
+    # harder sampling: few iterations allowed, high inlier bar -> several hypotheses are evaluated
+    kw2 = dict(solver=2, ransac_final=final, ransac_min_inliers_percentage=0.9999, ransac_max_iterations=7, ransac_seed=12345,
+               ransac_distance_threshold=0.05)
+    ctx.set_params(plo.default_params(**kw2))
+    ctx.project(np.eye(4))
+    delta2, info2 = ctx.solve_ransac()
+    ok, Do2 = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(**kw2))
+    assert info2["hypotheses"] == 7 and np.abs(delta2 - Do2).max() < 1e-9
+    # full loop (resident graph) against the oracle's loop with the same solver chain
+    ctx3, orc3 = _both(oracle_mod, pair.target, pair.source, **kw)
+    Tg, sg = ctx3.register()
+    To, so = orc3.register()
+    assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    # stepped driver with the reference's own config.json strings
+    cfg = plo.config.load_config()
+    cfg["laser_odometry"]["solve_method"]["method"] = "RANSAC"
+    cfg["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "Weighted LS" if final == 1 else "DRPM"
+    odo = plo.LaserOdometry(cfg, resident=False)
+    odo.process_frame(pair.target)
+    _, st = odo.process_frame(pair.source)
+    assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
