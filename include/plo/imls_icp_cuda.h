@@ -102,6 +102,52 @@ class IMLSICPMatcherCUDA {
     check(ctx_, plo_set_params(ctx_, &params_), "setLoopParameters");
   }
 
+  /* solve_method.method / solve_method.RANSAC.* of config.json (src/laser_odometry.cpp:606 -> :173-275,
+   * :196-244): picks the solver the resident loop (Match) and solveMotionEstimationProblem() below use.
+   * Accepted: "WeightedLS_CUDA" / "Weighted LS", "LS" / "LS_CUDA" (trimmed, src/solver.cpp:74-166),
+   * "RANSAC" with final_solve_method "Weighted LS" or "DRPM" (src/solver.cpp:222-385, :499-603).
+   * Anything else throws (the reference prints "Invalid SOLVE_METHOD!", :271). */
+  void setSolveMethod(const std::string& solve_method, double ls_threshold = 0.02, double ransac_distance_threshold = 0.8,
+                      double huber_threshold = 0.648, const std::string& final_solve_method = "DRPM",
+                      int ransac_max_iterations = 5000, double ransac_min_inliers_percentage = 0.95,
+                      double drpm_threshold = 0.05, double drpm_stdev_points = 0.02, double drpm_stdev_normals = 0.05) {
+    if (solve_method == "WeightedLS_CUDA" || solve_method == "Weighted LS") {
+      params_.solver = PLO_SOLVER_WLS;
+    } else if (solve_method == "LS" || solve_method == "LS_CUDA") {
+      params_.solver = PLO_SOLVER_LS;
+      params_.ls_threshold = ls_threshold;
+    } else if (solve_method == "RANSAC") {
+      params_.solver = PLO_SOLVER_RANSAC;
+      if (final_solve_method == "Weighted LS") params_.ransac_final = PLO_FINAL_WLS;
+      else if (final_solve_method == "DRPM") params_.ransac_final = PLO_FINAL_DRPM;
+      else throw std::runtime_error("plo: RANSAC final_solve_method \"" + final_solve_method + "\" does not run on the device");
+      params_.ransac_distance_threshold = ransac_distance_threshold;
+      params_.huber_threshold = huber_threshold;
+      params_.ransac_max_iterations = ransac_max_iterations;
+      params_.ransac_min_inliers_percentage = ransac_min_inliers_percentage;
+      params_.drpm_threshold = drpm_threshold;
+      params_.drpm_stdev_points = drpm_stdev_points;
+      params_.drpm_stdev_normals = drpm_stdev_normals;
+    } else {
+      throw std::runtime_error("plo: Invalid SOLVE_METHOD! (" + solve_method + ")");
+    }
+    check(ctx_, plo_set_params(ctx_, &params_), "setSolveMethod");
+  }
+
+  /* solveMotionEstimationProblem() (src/laser_odometry.cpp:173-275) for the selected method, on the
+   * device-resident pairs of the last ProjSourcePtToSurface (no vector round trip). */
+  template <typename Mat4T>
+  bool solveMotionEstimationProblem(Mat4T& deltaTrans) {
+    double D[16];
+    if (params_.solver == PLO_SOLVER_RANSAC) check(ctx_, plo_solve_ransac(ctx_, D, last_probs_, nullptr, nullptr), "solve (RANSAC)");
+    else if (params_.solver == PLO_SOLVER_LS) check(ctx_, plo_solve_ls(ctx_, D, nullptr), "solve (LS)");
+    else check(ctx_, plo_solve_wls(ctx_, D, nullptr), "solve (Weighted LS)");
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) deltaTrans(r, c) = D[r * 4 + c];
+    return true;
+  }
+  const double* lastDrpmProbabilities() const { return last_probs_; }
+
   /* include/imls_icp.h:79-82, src/imls_icp.cpp:496-745 (+ the transform of
    * src/laser_odometry.cpp:527-549).  in_cloud <- surviving transformed source points,
    * out_cloud <- projected points y with the matched normal; counters as printed at :736-744. */
@@ -156,6 +202,7 @@ class IMLSICPMatcherCUDA {
   plo_params params_;
   plo_proj_stats last_proj_{};
   plo_reg_stats last_reg_{};
+  double last_probs_[6] = {0, 0, 0, 0, 0, 0};
   std::vector<float> sx_, rx_, rn_;
   std::vector<int32_t> si_;
 };

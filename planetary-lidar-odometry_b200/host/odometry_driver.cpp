@@ -69,7 +69,16 @@ struct Config {
   }
   // value of the first occurrence of "key" after position of "scope" (enough for config.json's layout)
   std::string raw(const std::string& scope, const std::string& key, const std::string& dflt) const {
-    size_t p = scope.empty() ? 0 : text.find("\"" + scope + "\"");
+    size_t p = 0;
+    if (!scope.empty()) {   // the occurrence of "scope" that opens an object ("scope": {), not a string value
+      const std::string q = "\"" + scope + "\"";
+      for (p = text.find(q); p != std::string::npos; p = text.find(q, p + 1)) {
+        size_t c = text.find_first_not_of(" \t\r\n", p + q.size());
+        if (c == std::string::npos || text[c] != ':') continue;
+        c = text.find_first_not_of(" \t\r\n", c + 1);
+        if (c != std::string::npos && text[c] == '{') break;
+      }
+    }
     if (p == std::string::npos) return dflt;
     p = text.find("\"" + key + "\"", p);
     if (p == std::string::npos) return dflt;
@@ -130,8 +139,6 @@ int main(int argc, char** argv) {
     const std::string matching_method = cfg.raw("matching_method", "method", "IMLS");
     if (matching_method != "IMLS" && matching_method != "IMLS_CUDA") throw std::runtime_error("Invalid MATCHING_METHOD!");
     const std::string solve_method = cfg.raw("solve_method", "method", "WeightedLS_CUDA");
-    if (solve_method != "WeightedLS_CUDA" && solve_method != "Weighted LS" && solve_method != "LS_CUDA")
-      throw std::runtime_error("Invalid SOLVE_METHOD! (CUDA path: WeightedLS_CUDA)");
     const int iterations = (int)cfg.num("solve_method", "iterations", 30);
     const double h = cfg.num("IMLS", "h", 1), r = cfg.num("IMLS", "r", 3);
     const bool is_get_normals = cfg.flag("get_normals", "enabled", true);
@@ -149,6 +156,13 @@ int main(int argc, char** argv) {
     matcher.setParameters(iterations, h, r, r_normal, 0.8, false, is_get_normals, false, 50, 0.2, 0.6, search_number_normal,
                           search_number, normal_angle_constraint, angle_diff_threshold, "");   // :514-518
     matcher.setLoopParameters(transform_normal, correspond_number, delta_dist_threshold, delta_angle_threshold);
+    // :606 -> :173-275, parameters of :196-244; unknown / out-of-scope strings throw
+    matcher.setSolveMethod(solve_method, cfg.num("LS", "threshold", 0.02), cfg.num("RANSAC", "distance_threshold", 0.8),
+                           cfg.num("RANSAC", "huber_threshold", 0.648), cfg.raw("RANSAC", "final_solve_method", "DRPM"),
+                           (int)cfg.num("RANSAC", "max_iterations", 5000), cfg.num("RANSAC", "min_inliers_percentage", 0.95),
+                           cfg.num("RANSAC", "DRPM_threshold", 0.05), cfg.num("RANSAC", "DRPM_stdev_points", 0.02),
+                           cfg.num("RANSAC", "DRPM_stdev_normals", 0.05));
+    const bool host_vectors = solve_method == "WeightedLS_CUDA" || solve_method == "Weighted LS";
 
     std::ofstream poses(argv[3]);
     Matrix4d prevLaserPose;   // :48-57 globals
@@ -179,8 +193,10 @@ int main(int argc, char** argv) {
             }
             Matrix4d deltaTrans;
             std::vector<double> no_weights;
-            bool flag = plo::SolveMotionEstimationProblemWeightedLS_CUDA(matcher.context(), in_cloud_vec, ref_cloud_vec,
-                                                                         ref_normal, deltaTrans, no_weights, "");   // :609
+            bool flag = host_vectors
+                            ? plo::SolveMotionEstimationProblemWeightedLS_CUDA(matcher.context(), in_cloud_vec, ref_cloud_vec,
+                                                                               ref_normal, deltaTrans, no_weights, "")   // :609
+                            : matcher.solveMotionEstimationProblem(deltaTrans);   // LS / RANSAC on the resident pairs
             if (!flag) break;                                                   // :611-616
             rPose = deltaTrans * rPose;                                         // :619
             ++iters;

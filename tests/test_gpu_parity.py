@@ -449,6 +449,30 @@ def test_cpp_host_driver_matches_python_driver(tmp_path):
         got = np.loadtxt(out)
         assert got.shape == (3, 8)
         assert np.abs(got[:, 1:4] - P[:, :3, 3]).max() < 2e-6      # 6 decimals in the TUM file
+    # the reference's own config.json layout with its default solver chain strings (RANSAC -> DRPM / Weighted LS);
+    # "Ceres.max_iterations" precedes "RANSAC.max_iterations" as in the reference file
+    import json
+    for final in ("Weighted LS", "DRPM"):
+        cfg = plo.config.load_config()
+        sm = cfg["laser_odometry"]["solve_method"]
+        sm_new = {"_comment": "choose method: Ceres, LS, RANSAC, ICP, Teaser", "method": "RANSAC"}
+        sm_new.update({k: v for k, v in sm.items() if k not in ("method", "RANSAC", "LS")})
+        sm_new["Ceres"] = {"max_iterations": 20}
+        sm_new["LS"] = {"threshold": 0.02}
+        sm_new["RANSAC"] = {"max_iterations": 5000, "distance_threshold": 0.8, "min_inliers_percentage": 0.95,
+                            "huber_threshold": 0.648, "final_solve_method": final, "LS_threshold": 0.02,
+                            "DRPM_threshold": 0.05, "DRPM_stdev_points": 0.02, "DRPM_stdev_normals": 0.05}
+        cfg["laser_odometry"]["solve_method"] = sm_new
+        cfn = str(tmp_path / "config.json")
+        with open(cfn, "w", encoding="utf-8") as f:
+            json.dump(cfg, f, indent=4)
+        Pr = plo.LaserOdometry(plo.config.load_config(cfn), resident=True).run(frames)
+        for mode in ("resident", "stepped"):
+            out = str(tmp_path / f"poses_ransac_{mode}.txt")
+            subprocess.check_call([exe, cfn, mode, out] + files)
+            got = np.loadtxt(out)
+            assert np.abs(got[:, 1:4] - Pr[:, :3, 3]).max() < 2e-6
+        assert np.abs(Pr - P).max() > 1e-9      # a different solver really ran
 
 
 def test_cfg2_vlp32c_sequence_full_size(oracle_mod):
