@@ -634,6 +634,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   }
 }
 
+#include "knn_project_tile.cuh"
+
 // ---- PCA normals: IMLSICPMatcher::ComputeNormal (src/imls_icp.cpp:753-794) -------------
 
 // cyclic Jacobi on a symmetric 3x3; returns the unit eigenvector of the smallest eigenvalue
@@ -768,6 +770,40 @@ void launch_project_levels(plo_ctx* c, int blocks, const ProjectOut& out, int ch
     default: k_project<PCA, 6, HOOKS><<<blocks, T, 0, c->stream>>>(mv, sp, sn, dc, st, c->dprm, out, chunk, cc); break;
   }
 }
+template <bool PCA, int LEVELS, bool HOOKS>
+cudaError_t launch_tile_one(plo_ctx* c, const ProjectOut& out) {
+  auto kern = k_project_tile<PCA, LEVELS, HOOKS>;
+  const size_t smem = tile_warp_bytes(c->dprm.k) * kTileWarps;
+  static size_t smem_set = 0;   // per instantiation
+  if (smem > smem_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWarps * 32, smem);
+  if (e != cudaSuccess) return e;
+  const int64_t tiles = (c->m_raw + 31) / 32;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + kTileWarps - 1) / kTileWarps,
+                                                                (int64_t)c->sm_count * std::max(per_sm, 1)));
+  kern<<<blocks, kTileWarps * 32, smem, c->stream>>>(c->map_view(), c->s_p.as<float4>(), c->s_n.as<float4>(), c->s_order.as<int>(),
+                                                      c->counts.as<DevCounts>(), c->state.as<DevState>(), c->dprm, out,
+                                                      c->chunk_counter.as<int>());
+  return cudaGetLastError();
+}
+
+template <bool PCA, bool HOOKS>
+cudaError_t launch_tile_levels(plo_ctx* c, const ProjectOut& out) {
+  switch (c->n_levels) {
+    case 0:
+    case 1: return launch_tile_one<PCA, 1, HOOKS>(c, out);
+    case 2: return launch_tile_one<PCA, 2, HOOKS>(c, out);
+    case 3: return launch_tile_one<PCA, 3, HOOKS>(c, out);
+    case 4: return launch_tile_one<PCA, 4, HOOKS>(c, out);
+    case 5: return launch_tile_one<PCA, 5, HOOKS>(c, out);
+    default: return launch_tile_one<PCA, 6, HOOKS>(c, out);
+  }
+}
 }  // namespace
 
 int plo_launch_project(plo_ctx* c, bool hooks) {
@@ -779,6 +815,15 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
   out.search_stats = c->q_stats.as<int>();
+  if (c->tile_mode) {   // lane-per-query kernel over Hilbert-ordered tiles of the source (knn_project_tile.cuh)
+    PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
+    PLO_CUDA(c, cudaMemsetAsync(c->chunk_counter.p, 0, sizeof(int), c->stream));
+    if (c->dprm.use_pca_normals) PLO_CUDA(c, (hooks ? launch_tile_levels<true, true>(c, out) : launch_tile_levels<true, false>(c, out)));
+    else PLO_CUDA(c, (hooks ? launch_tile_levels<false, true>(c, out) : launch_tile_levels<false, false>(c, out)));
+    c->prev_valid = true;
+    c->launches++;
+    return PLO_OK;
+  }
   // persistent grid (PLO_MINB blocks per SM); chunks of consecutive source points are fetched through
   // an atomic counter.  The chunk length comes from the device-side loop state (see k_solve_update)
   // unless the cloud is too small to fill the GPU (then 1) or the tuning knob overrides it.

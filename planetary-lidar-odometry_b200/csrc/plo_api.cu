@@ -519,6 +519,7 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   add(c->stream);
   add(c->pts_sorted.p); add(c->nrm_sorted.p); add(c->nrm_pca.p);
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
+  add(c->s_order.p); v.push_back(c->tile_mode ? 1ull : 0ull);
   add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p);
   add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
   add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);

@@ -134,6 +134,8 @@ struct plo_ctx {
   int64_t m_raw = 0;
   bool have_source = false;
   DevBuf s_stage, s_stage2, s_praw, s_nraw, s_p, s_n;
+  DevBuf s_cidx, s_bbox, s_order;   // tile kernel: stripped index of every raw point, bounding box, Hilbert order
+  bool tile_mode = false;           // the source is large enough for the lane-per-query kernel (s_order valid)
 
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
@@ -191,7 +193,7 @@ static inline int plo_grid(const plo_ctx* c, int blocks_per_sm) { return c->sm_c
 int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
 int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride);
 int plo_sort_pairs(plo_ctx* c, unsigned long long* keys[2], int* vals[2], int64_t n, int passes, int* hist, int* digit_total,
-                   int* out_which);
+                   int* out_which, int first_shift = 0);
 size_t plo_sort_hist_ints(int64_t n);
 size_t plo_sort_total_ints(int passes);
 // ---- knn_project.cu ---------------------------------------------------------------

@@ -649,3 +649,36 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     odo.process_frame(pair.target)
     _, st = odo.process_frame(pair.source)
     assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
+
+
+def test_tile_kernel_parity(oracle_mod, monkeypatch):
+    """PLO_PROJECT=tile: the experimental lane-per-query projection kernel (csrc/knn_project_tile.cuh) is held to
+    the same bars as the default one — neighbour sets, d2, statuses, drop counters bit-exact, heights to tolerance,
+    the resident loop to the pose tolerance — on an urban pair, ragged sizes, coincident points and NaN inputs."""
+    monkeypatch.setenv("PLO_PROJECT", "tile")
+    pair = W.hdl64_pair(max_source=20000)
+    ctx, orc = _both(oracle_mod, pair.target, pair.source)
+    _check_projection(ctx, orc)
+    _check_projection(ctx, orc, T=pair.T_gt)            # second projection: temporal bounds in play
+    Tg, sg = ctx.register()
+    To, so = orc.register()
+    assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    ctx2, orc2 = _both(oracle_mod, pair.target[::3], pair.source[::10], search_number=32, r=1.5, h=0.7)
+    _check_projection(ctx2, orc2)
+    rng = np.random.default_rng(77)
+    for n_t, n_s in ((1, 1), (31, 7), (33, 64), (1025, 100), (5000, 333)):
+        tgt = np.zeros((n_t, 12), np.float32)
+        tgt[:, 0:3] = rng.uniform(-2, 2, size=(n_t, 3))
+        tgt[:, 4:7] = [0, 0, 1]
+        src = np.zeros((n_s, 12), np.float32)
+        src[:, 0:3] = rng.uniform(-2, 2, size=(n_s, 3))
+        src[:, 4:7] = [0, 0, 1]
+        if n_s > 50:
+            src[3, 0] = np.nan                           # stripped: later indices shift
+            src[7, 0:3] = tgt[5, 0:3]                    # coincident with a map point: self-match rule of the 1-NN
+        if n_t > 1000:
+            tgt[100:160, 0:3] = tgt[100, 0:3]            # 60 coincident map points: ties by index, 1-NN fallback
+            src[11, 0:3] = tgt[100, 0:3]
+        c3, o3 = _both(oracle_mod, tgt, src)
+        _check_projection(c3, o3)
