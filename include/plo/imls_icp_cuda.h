@@ -192,6 +192,17 @@ class IMLSICPMatcherCUDA {
     return last_reg_.status == PLO_REG_CONVERGED || last_reg_.status == PLO_REG_MAX_ITERS;
   }
 
+  /* accumulateTargetCloud (src/laser_odometry.cpp:116-136) with the TransformToEnd step the reference left
+   * commented out (:118-124): the queue lives on the device, every queued frame moves into the new frame's
+   * coordinates with the pose still resident from the last Match(), only `newCloud` crosses the bus, and the
+   * result is the target of the next frame (no setTargetPointCloud call).  first_frame: nothing registered yet. */
+  template <typename CloudPtr>
+  void accumulateTargetCloud(const CloudPtr& newCloud, size_t max_queue_size, bool transform_normal, bool first_frame) {
+    check(ctx_, plo_map_push(ctx_, newCloud->points.data(), (int64_t)newCloud->points.size(), (int32_t)sizeof(PointT), nullptr,
+                             first_frame ? 0 : 1, (int32_t)max_queue_size, transform_normal ? 1 : 0),
+          "accumulateTargetCloud");
+  }
+
   const std::vector<int32_t>& srcIndices() const { return si_; }
   const plo_proj_stats& lastProjection() const { return last_proj_; }
   const plo_reg_stats& lastRegistration() const { return last_reg_; }

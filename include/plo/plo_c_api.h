@@ -239,6 +239,28 @@ PLO_API int plo_register_batch(plo_ctx* ctx, int32_t count,
                                int32_t stride_bytes, int32_t on_device,
                                double* T_out, plo_reg_stats* stats_out);
 
+/* ---- device-resident local map --------------------------------
+ * accumulateTargetCloud (src/laser_odometry.cpp:116-136) with the TransformToEnd step (:88-114) that the
+ * reference left commented out (:118-124), so that a queue of more than one frame is geometrically
+ * consistent.  plo_map_push: (1) every queued frame moves from the previous frame's coordinates into the
+ * new frame's, p' = R^T (p - t) in double with a float32 store (normals too when transform_normals != 0),
+ * where [R t] = T_last_curr is the rPose of the registration just done (x_prev = R x_cur + t; NULL =
+ * identity), or — pose_from_last_register != 0 — the pose still resident on the device after
+ * plo_register, which keeps register -> push -> register free of host round trips; (2) frames beyond
+ * max_queue (config.json laser_odometry.max_queue_size) drop out, oldest first; (3) the new frame is
+ * appended; (4) the result becomes the target (index rebuilt on the device, as plo_set_target).
+ * Only the new frame ever crosses the bus.  plo_map_reset empties the queue. */
+PLO_API int plo_map_reset(plo_ctx* ctx);
+PLO_API int plo_map_push(plo_ctx* ctx, const void* host_pts, int64_t n, int32_t stride_bytes, const double T_last_curr[16],
+                         int32_t pose_from_last_register, int32_t max_queue, int32_t transform_normals);
+PLO_API int plo_map_push_device(plo_ctx* ctx, const void* dev_pts, int64_t n, int32_t stride_bytes,
+                                const double T_last_curr[16], int32_t pose_from_last_register, int32_t max_queue,
+                                int32_t transform_normals);
+/* queued frames / points (before the non-finite strip) */
+PLO_API int plo_map_info(plo_ctx* ctx, int32_t* frames, int64_t* points);
+/* the map as 32-byte records {x,y,z,0,nx,ny,nz,0} (floats), oldest frame first; cap in records */
+PLO_API int plo_map_get(plo_ctx* ctx, float* records8, int64_t cap);
+
 /* ---- introspection (bench / tests) ------------------------------------------------ */
 /* kernels launched by this context since creation (bench.py's gpu_launches claim) */
 PLO_API int64_t plo_launch_count(const plo_ctx* ctx);

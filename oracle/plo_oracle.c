@@ -304,6 +304,25 @@ int orc_knn_brute(const orc_ctx* c, const double q[3], int k, double r, int allo
 
 static inline int finite3f(const float* p) { return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]); }
 
+/* TransformToEnd, src/laser_odometry.cpp:88-114 (see plo_oracle.h) */
+void orc_transform_to_end(void* pts, int64_t n, int32_t stride, const double T[16], int transform_normal) {
+  char* base = (char*)pts;
+  for (int64_t i = 0; i < n; ++i) {
+    float* p = (float*)(base + i * stride);
+    const double dx = (double)p[0] - T[3], dy = (double)p[1] - T[7], dz = (double)p[2] - T[11];
+    p[0] = (float)((T[0] * dx + T[4] * dy) + T[8] * dz); /* row a of R^T = column a of R */
+    p[1] = (float)((T[1] * dx + T[5] * dy) + T[9] * dz);
+    p[2] = (float)((T[2] * dx + T[6] * dy) + T[10] * dz);
+    if (transform_normal) {
+      float* nn = (float*)(base + i * stride + 16);
+      const double a = (double)nn[0], b = (double)nn[1], c = (double)nn[2];
+      nn[0] = (float)((T[0] * a + T[4] * b) + T[8] * c);
+      nn[1] = (float)((T[1] * a + T[5] * b) + T[9] * c);
+      nn[2] = (float)((T[2] * a + T[6] * b) + T[10] * c);
+    }
+  }
+}
+
 /* src/imls_icp.cpp:80-103 (+ RemoveNANandINFData :58-72; pcl::isFinite tests xyz only) */
 int64_t orc_set_target(orc_ctx* c, const void* pts, int64_t n, int32_t stride) {
   free_target(c);

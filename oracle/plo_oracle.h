@@ -105,6 +105,12 @@ int orc_get_threads(const orc_ctx* c);
  * receives original index of each kept point. */
 int64_t orc_set_target(orc_ctx* c, const void* pts, int64_t n, int32_t stride);
 int64_t orc_set_source(orc_ctx* c, const void* pts, int64_t n, int32_t stride);
+/* TransformToEnd, src/laser_odometry.cpp:88-114 — the step the reference left commented out in
+ * accumulateTargetCloud (:118-124): bring a cloud expressed in the previous frame into the current frame,
+ * given rPose = [R t] of the registration just done (x_prev = R x_cur + t):  p' = R^-1 (p - t), and
+ * n' = R^-1 n when transform_normal.  Double arithmetic, float32 store, in place.  R^-1 is taken as R^T
+ * (the reference goes through a quaternion, q_last_curr.inverse().toRotationMatrix()). */
+void orc_transform_to_end(void* pts, int64_t n, int32_t stride, const double T[16], int transform_normal);
 int64_t orc_target_size(const orc_ctx* c);
 int64_t orc_source_size(const orc_ctx* c);
 /* target normals actually used (PCA when !is_get_normals): n x 3 doubles */

@@ -220,6 +220,17 @@ class Oracle:
                                      counters=np.array(list(st.counters), np.int64), per_iter_pairs=per)
 
 
+def transform_to_end(rec: np.ndarray, T, transform_normal: bool = False) -> np.ndarray:
+    """TransformToEnd (src/laser_odometry.cpp:88-114) on a copy of float32 records (n x 12)."""
+    out = np.ascontiguousarray(rec, dtype=np.float32).copy()
+    T = _f64(T).reshape(16)
+    L = lib()
+    L.orc_transform_to_end.restype = None
+    L.orc_transform_to_end.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int]
+    L.orc_transform_to_end(_p(out), out.shape[0], out.strides[0], _p(T), int(bool(transform_normal)))
+    return out
+
+
 def solve_wls(src, ref, nrm, w=None):
     src, ref, nrm = _f64(src), _f64(ref), _f64(nrm)
     w = None if w is None else _f64(w)

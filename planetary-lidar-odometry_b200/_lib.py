@@ -60,7 +60,7 @@ EXPORTS = [
     "plo_get_neighbors", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls", "plo_solve_ls", "plo_solve_ransac",
     "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
-    "plo_last_kernel_timings",
+    "plo_last_kernel_timings", "plo_map_reset", "plo_map_push", "plo_map_push_device", "plo_map_info", "plo_map_get",
 ]
 
 
@@ -117,6 +117,11 @@ def lib() -> C.CDLL:
     L.plo_time_project_kernel.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
     L.plo_set_profiling.argtypes = [vp, i32]
     L.plo_last_kernel_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.plo_map_reset.argtypes = [vp]
+    L.plo_map_push.argtypes = [vp, vp, i64, i32, vp, i32, i32, i32]
+    L.plo_map_push_device.argtypes = [vp, vp, i64, i32, vp, i32, i32, i32]
+    L.plo_map_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
+    L.plo_map_get.argtypes = [vp, vp, i64]
     _lib = L
     return L
 

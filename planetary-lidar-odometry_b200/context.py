@@ -101,6 +101,33 @@ class Context:
         self._keep_s = keep
         self._ck((self.L.plo_set_source_device if dev else self.L.plo_set_source)(self.h, p, n, stride))
 
+    # -- device-resident local map (plo_map_*) -------------------------------------------
+    def map_reset(self):
+        self._ck(self.L.plo_map_reset(self.h))
+
+    def map_push(self, rec, T_last_curr=None, from_last_register: bool = False, max_queue: int = 1,
+                 transform_normals: bool = False):
+        """accumulateTargetCloud with TransformToEnd (src/laser_odometry.cpp:116-136, :88-114): the queued frames
+        move into the new frame's coordinates, the new frame is appended, the index is rebuilt on the device."""
+        p, n, stride, dev, keep = _records(rec)
+        self._keep_t = keep
+        T = None if T_last_curr is None else np.ascontiguousarray(T_last_curr, dtype=np.float64).reshape(16)
+        fn = self.L.plo_map_push_device if dev else self.L.plo_map_push
+        self._ck(fn(self.h, p, n, stride, _ptr(T), 1 if from_last_register else 0, int(max_queue), 1 if transform_normals else 0))
+
+    def map_info(self):
+        fr, pts = C.c_int32(), C.c_int64()
+        self._ck(self.L.plo_map_info(self.h, C.byref(fr), C.byref(pts)))
+        return fr.value, pts.value
+
+    def map_records(self) -> np.ndarray:
+        """(n, 8) float32: x y z 0 nx ny nz 0, oldest frame first, in the newest frame's coordinates"""
+        _, n = self.map_info()
+        out = np.zeros((n, 8), np.float32)
+        if n:
+            self._ck(self.L.plo_map_get(self.h, _ptr(out), n))
+        return out
+
     @property
     def n_target(self) -> int:
         return int(self.L.plo_target_size(self.h))

@@ -401,6 +401,56 @@ __global__ void __launch_bounds__(256) k_source_order(const int* __restrict__ va
   if (t < n) order[t] = cidx[vals_sorted[t]];
 }
 
+// ---- local map: TransformToEnd of src/laser_odometry.cpp:88-114 on the device ----
+
+struct MapPose { double m[12]; };   // rows of [R t]: x_prev = R x_cur + t (rPose of the registration just done)
+
+// kept frames: p' = R^T (p - t) in double, float32 store (and n' = R^T n when asked), written to the front of `out`
+__global__ void __launch_bounds__(256) k_map_advance(const float4* __restrict__ in, int64_t n, float4* __restrict__ out,
+                                                     const DevState* __restrict__ st, MapPose P, int identity,
+                                                     int transform_normals) {
+  __shared__ double T[12];
+  if (threadIdx.x < 12) T[threadIdx.x] = st ? st->rPose[threadIdx.x] : P.m[threadIdx.x];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float4 a = in[2 * i], b = in[2 * i + 1];
+    if (!identity) {
+      const double dx = __dsub_rn((double)a.x, T[3]), dy = __dsub_rn((double)a.y, T[7]), dz = __dsub_rn((double)a.z, T[11]);
+      a.x = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], dx), __dmul_rn(T[4], dy)), __dmul_rn(T[8], dz)));
+      a.y = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[1], dx), __dmul_rn(T[5], dy)), __dmul_rn(T[9], dz)));
+      a.z = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[2], dx), __dmul_rn(T[6], dy)), __dmul_rn(T[10], dz)));
+      if (transform_normals) {
+        const double u = (double)b.x, v = (double)b.y, w = (double)b.z;
+        b.x = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], u), __dmul_rn(T[4], v)), __dmul_rn(T[8], w)));
+        b.y = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[1], u), __dmul_rn(T[5], v)), __dmul_rn(T[9], w)));
+        b.z = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[2], u), __dmul_rn(T[6], v)), __dmul_rn(T[10], w)));
+      }
+    }
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+  }
+}
+
+// new frame: caller's records -> packed 32-byte records behind the kept ones
+__global__ void __launch_bounds__(256) k_map_append(const char* __restrict__ rec, int stride, int64_t n, int vec16,
+                                                    float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float4 a, b;
+    if (vec16) {
+      a = *reinterpret_cast<const float4*>(rec + (size_t)i * stride);
+      b = *reinterpret_cast<const float4*>(rec + (size_t)i * stride + 16);
+    } else {
+      const float* r = reinterpret_cast<const float*>(rec + (size_t)i * stride);
+      a = make_float4(r[0], r[1], r[2], 0.f);
+      b = make_float4(r[4], r[5], r[6], 0.f);
+    }
+    a.w = 0.f;
+    b.w = 0.f;
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+  }
+}
+
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
@@ -600,4 +650,47 @@ int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t st
   }
   c->have_source = true;
   return PLO_OK;
+}
+
+// Local map push (accumulateTargetCloud, src/laser_odometry.cpp:116-136, WITH the TransformToEnd step the reference
+// left commented out at :118-124): the queued frames move into the new frame's coordinates, the oldest frames beyond
+// max_queue drop out, the new frame is appended, and the index is rebuilt over the result — all on the device, no
+// host synchronisation.  The pose comes from the host (T) or straight from the device-resident loop state of the
+// registration just done (pose_from_device), which keeps register -> push -> register free of host round trips.
+int plo_map_push_records(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const double* T_host_or_null,
+                         bool pose_from_device, int32_t max_queue, bool transform_normals) {
+  if (max_queue < 1) max_queue = 1;
+  int64_t total = 0;
+  for (int64_t f : c->map_frames) total += f;
+  int64_t drop = 0;
+  while ((int64_t)c->map_frames.size() + 1 > max_queue && !c->map_frames.empty()) {
+    drop += c->map_frames.front();
+    c->map_frames.erase(c->map_frames.begin());
+  }
+  const int64_t keep = total - drop;
+  const int64_t new_total = keep + n;
+  if (new_total > (int64_t)1 << 30) return plo_fail(c, PLO_ERR_UNSUPPORTED, "local map larger than 2^30 points");
+  DevBuf& src = c->map_rec[c->map_cur];
+  DevBuf& dst = c->map_rec[c->map_cur ^ 1];
+  PLO_CUDA(c, dst.reserve(sizeof(float4) * 2 * (size_t)std::max<int64_t>(new_total, 1)));
+  cudaStream_t s = c->stream;
+  if (keep > 0) {
+    MapPose P;
+    const bool identity = !pose_from_device && T_host_or_null == nullptr;
+    for (int i = 0; i < 12; ++i) P.m[i] = T_host_or_null ? T_host_or_null[i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    const int blocks = (int)std::min<int64_t>((keep + 255) / 256, (int64_t)plo_grid(c, 8));
+    k_map_advance<<<blocks, 256, 0, s>>>(src.as<float4>() + 2 * drop, keep, dst.as<float4>(),
+                                         pose_from_device ? c->state.as<DevState>() : nullptr, P, identity ? 1 : 0,
+                                         transform_normals ? 1 : 0);
+    LAUNCH_CHECK(c);
+  }
+  if (n > 0) {
+    const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)plo_grid(c, 8));
+    k_map_append<<<blocks, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, n, vec16, dst.as<float4>() + 2 * keep);
+    LAUNCH_CHECK(c);
+  }
+  c->map_cur ^= 1;
+  c->map_frames.push_back(n);
+  return plo_build_index(c, dst.p, new_total, 32);
 }

@@ -179,7 +179,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
@@ -278,6 +278,63 @@ int plo_set_source_device(plo_ctx* c, const void* dev_pts, int64_t n, int32_t st
   if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_source_device: bad stride");
   PLO_CUDA(c, cudaSetDevice(c->device));
   return plo_upload_source(c, dev_pts, n, stride);
+}
+
+int plo_map_reset(plo_ctx* c) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  c->map_frames.clear();
+  return PLO_OK;
+}
+
+static int map_push_common(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const double* T_last_curr,
+                           int32_t pose_from_last_register, int32_t max_queue, int32_t transform_normals) {
+  if (pose_from_last_register && !c->projected)
+    return plo_fail(c, PLO_ERR_STATE, "plo_map_push: pose_from_last_register without a registration on this context");
+  return plo_map_push_records(c, dev_records, n, stride, pose_from_last_register ? nullptr : T_last_curr,
+                              pose_from_last_register != 0, max_queue, transform_normals != 0);
+}
+
+int plo_map_push(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride, const double* T_last_curr,
+                 int32_t pose_from_last_register, int32_t max_queue, int32_t transform_normals) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !host_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_push: bad pointer / count");
+  if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_push: stride must be >= 28 and a multiple of 4");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  if (n > 0) {
+    PLO_CUDA(c, c->t_stage.reserve((size_t)n * stride));
+    PLO_CUDA(c, cudaMemcpyAsync(c->t_stage.p, host_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+  }
+  return map_push_common(c, c->t_stage.p, n, stride, T_last_curr, pose_from_last_register, max_queue, transform_normals);
+}
+
+int plo_map_push_device(plo_ctx* c, const void* dev_pts, int64_t n, int32_t stride, const double* T_last_curr,
+                        int32_t pose_from_last_register, int32_t max_queue, int32_t transform_normals) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !dev_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_push_device: bad pointer / count");
+  if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_push_device: bad stride");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  return map_push_common(c, dev_pts, n, stride, T_last_curr, pose_from_last_register, max_queue, transform_normals);
+}
+
+int plo_map_info(plo_ctx* c, int32_t* frames, int64_t* points) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  int64_t total = 0;
+  for (int64_t f : c->map_frames) total += f;
+  if (frames) *frames = (int32_t)c->map_frames.size();
+  if (points) *points = total;
+  return PLO_OK;
+}
+
+int plo_map_get(plo_ctx* c, float* records8, int64_t cap) {
+  if (!c || !records8) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_get: NULL argument");
+  int64_t total = 0;
+  for (int64_t f : c->map_frames) total += f;
+  if (cap < total) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_map_get: buffer too small");
+  if (total == 0) return PLO_OK;
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaMemcpyAsync(records8, c->map_rec[c->map_cur].p, sizeof(float) * 8 * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
 }
 
 static int fetch_counts(plo_ctx* c) {

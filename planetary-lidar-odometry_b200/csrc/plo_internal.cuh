@@ -137,6 +137,12 @@ struct plo_ctx {
   DevBuf s_cidx, s_bbox, s_order;   // tile kernel: stripped index of every raw point, bounding box, Hilbert order
   bool tile_mode = false;           // the source is large enough for the lane-per-query kernel (s_order valid)
 
+  // device-resident local map (plo_map_push): frames back to back as 32-byte records {x,y,z,-,nx,ny,nz,-},
+  // all expressed in the frame of the most recent push; two buffers, swapped on every push
+  DevBuf map_rec[2];
+  int map_cur = 0;
+  std::vector<int64_t> map_frames;   // points per queued frame, oldest first
+
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
   bool prev_valid = false;   // q_x / q_kd2 hold the previous projection of the SAME clouds and k, r
@@ -196,6 +202,8 @@ int plo_sort_pairs(plo_ctx* c, unsigned long long* keys[2], int* vals[2], int64_
                    int* out_which, int first_shift = 0);
 size_t plo_sort_hist_ints(int64_t n);
 size_t plo_sort_total_ints(int passes);
+int plo_map_push_records(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const double* T_host_or_null,
+                         bool pose_from_device, int32_t max_queue, bool transform_normals);
 // ---- knn_project.cu ---------------------------------------------------------------
 int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);

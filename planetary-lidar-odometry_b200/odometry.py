@@ -8,6 +8,13 @@ nowPose = prevLaserPose * rPose (:649-655).  Two loop modes:
   resident=False  the reference's own structure: ProjSourcePtToSurface -> getXYZ/getNormals ->
                   solveMotionEstimationProblem -> rPose = deltaTrans * rPose, one host round
                   trip per iteration (boundary-parity mode, used by the tests)
+Two target modes (accumulateTargetCloud, :116-136):
+  map_mode="reference"   the reference's live code: the queued clouds are concatenated as they are
+                         (only right for max_queue_size = 1, the config.json default)
+  map_mode="consistent"  the TransformToEnd step the reference left commented out (:118-124) is applied: the
+                         queue lives on the device (plo_map_push), every queued frame is moved into the newest
+                         frame's coordinates with the pose still resident from plo_register, only the new frame
+                         crosses the bus, the index is rebuilt on the device
 """
 from __future__ import annotations
 
@@ -21,7 +28,8 @@ from .matcher import IMLSICPMatcher
 
 
 class LaserOdometry:
-    def __init__(self, cfg: dict | None = None, device: int = 0, resident: bool = True, ctx: Context | None = None):
+    def __init__(self, cfg: dict | None = None, device: int = 0, resident: bool = True, ctx: Context | None = None,
+                 map_mode: str = "reference", map_transform_normals: bool = True):
         self.cfg = cfg or _config.load_config()
         self.params = _config.params_from_config(self.cfg)
         self.ctx = ctx or Context(device, self.params)
@@ -29,6 +37,12 @@ class LaserOdometry:
             self.ctx.set_params(self.params)
         self.matcher = IMLSICPMatcher(ctx=self.ctx)
         self.resident = resident
+        if map_mode not in ("reference", "consistent"):
+            raise ValueError(f"map_mode {map_mode!r}: 'reference' or 'consistent'")
+        self.map_mode = map_mode
+        self.map_transform_normals = map_transform_normals
+        if map_mode == "consistent":
+            self.ctx.map_reset()
         self.max_queue_size = int(self.cfg["laser_odometry"].get("max_queue_size", 1))
         self.cloudQueue = collections.deque()
         self.prevLaserPose = np.eye(4)
@@ -75,9 +89,11 @@ class LaserOdometry:
         normals), flat_cloud = /laser_cloud_flat (sampled source; default: the full cloud)."""
         flat_cloud = filtered_cloud if flat_cloud is None else flat_cloud
         stats = None
+        consistent = self.map_mode == "consistent"
         if self.frameCount != 0:                                   # :478
             self.matcher.setSourcePointCloud(flat_cloud)           # :509
-            self.matcher.setTargetPointCloud(self._target)         # :510
+            if not consistent:
+                self.matcher.setTargetPointCloud(self._target)     # :510 (consistent: the device map is the target)
             if self.resident:
                 rPose, stats = self.ctx.register(None)             # :484-485 identity start
             else:
@@ -87,7 +103,17 @@ class LaserOdometry:
             stats["rPose"] = rPose
         self.poses.append(self.prevLaserPose.copy())
         self.frame_stats.append(stats)
-        self._target = self._accumulate(filtered_cloud)            # :668-670
+        if consistent:                                             # :668-670 with TransformToEnd (:118-124)
+            if stats is None:
+                self.ctx.map_push(filtered_cloud, None, max_queue=self.max_queue_size)
+            elif self.resident:
+                self.ctx.map_push(filtered_cloud, from_last_register=True, max_queue=self.max_queue_size,
+                                  transform_normals=self.map_transform_normals)
+            else:
+                self.ctx.map_push(filtered_cloud, stats["rPose"], max_queue=self.max_queue_size,
+                                  transform_normals=self.map_transform_normals)
+        else:
+            self._target = self._accumulate(filtered_cloud)        # :668-670
         self.frameCount += 1
         return self.prevLaserPose.copy(), stats
 

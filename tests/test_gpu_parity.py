@@ -682,3 +682,75 @@ def test_tile_kernel_parity(oracle_mod, monkeypatch):
             src[11, 0:3] = tgt[100, 0:3]
         c3, o3 = _both(oracle_mod, tgt, src)
         _check_projection(c3, o3)
+
+
+def test_local_map_transform_is_bit_exact_and_drops_oldest(oracle_mod):
+    """plo_map_push against the oracle's TransformToEnd (src/laser_odometry.cpp:88-114): float32 records bit-exact,
+    queue bounded by max_queue (oldest frame first out), the map becomes the target."""
+    seq = W.Sequence(seed=2003, n_frames=4, max_points=6000)
+    frames = [seq.frame(k).astype(np.float32) for k in range(4)]
+    frames[1][5, 0] = np.nan                                        # non-finite points ride along and are stripped by the index
+    rng = np.random.default_rng(5)
+    ctx = plo.Context(0)
+    queue = []
+    for k, f in enumerate(frames):
+        T = None
+        if k > 0:
+            T = W.scenes.pose_matrix(rng.uniform(-0.8, 0.8, 3), yaw_deg=rng.uniform(-3, 3), pitch_deg=rng.uniform(-1, 1),
+                                     roll_deg=rng.uniform(-1, 1))
+        for tn in (True,):
+            ctx.map_push(f, T, max_queue=3, transform_normals=tn)
+        if T is not None:
+            queue = [oracle_mod.transform_to_end(q, T, True) for q in queue]
+        queue.append(f.copy())
+        queue = queue[-3:]
+        want = np.concatenate(queue, axis=0)
+        got = ctx.map_records()
+        assert ctx.map_info() == (len(queue), want.shape[0])
+        assert np.array_equal(got[:, 0:3], want[:, 0:3], equal_nan=True)
+        assert np.array_equal(got[:, 4:7], want[:, 4:7], equal_nan=True)
+        assert ctx.n_target == int(np.isfinite(want[:, 0:3]).all(axis=1).sum())
+    # normals stay untouched without transform_normals
+    ctx2 = plo.Context(0)
+    ctx2.map_push(frames[0], None, max_queue=2)
+    ctx2.map_push(frames[1], T, max_queue=2, transform_normals=False)
+    got = ctx2.map_records()
+    assert np.array_equal(got[:frames[0].shape[0], 4:7], frames[0][:, 4:7])
+    assert np.array_equal(got[:frames[0].shape[0], 0:3], oracle_mod.transform_to_end(frames[0], T, False)[:, 0:3])
+
+
+def test_consistent_local_map_odometry(oracle_mod):
+    """a pose-consistent multi-frame local map (max_queue_size = 3) kept on the device.
+    Against the same loop on the oracle (register, TransformToEnd of the queue, append), and against ground truth,
+    where the reference's untransformed concatenation is visibly worse."""
+    seq = W.Sequence(seed=2004, n_frames=5, max_points=12000)
+    frames = [seq.frame(k) for k in range(5)]
+    cfg = plo.config.load_config()
+    cfg["laser_odometry"]["max_queue_size"] = 3
+    odo = plo.LaserOdometry(cfg, resident=True, map_mode="consistent")
+    odo.process_frame(frames[0])
+    odo_h = plo.LaserOdometry(cfg, resident=False, map_mode="consistent")      # pose handed over by the host instead
+    odo_h.run(frames)
+    orc = oracle_mod.Oracle()
+    queue = [np.asarray(frames[0], np.float32)]
+    for k in range(1, 5):
+        orc.set_target(np.concatenate(queue, axis=0))
+        orc.set_source(frames[k])
+        To, so = orc.register()
+        _, st = odo.process_frame(frames[k])
+        assert st["iters"] == so["iters"] and st["status"] == so["status"] and st["pairs"] == so["pairs"], k
+        assert _rot_err(st["rPose"][:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(st["rPose"][:3, 3] - To[:3, 3]) < POSE_M
+        assert np.abs(odo_h.frame_stats[k]["rPose"] - st["rPose"]).max() < 1e-7
+        # the oracle's queue advances with the GPU's pose, so that both sides keep registering the same bytes
+        queue = [oracle_mod.transform_to_end(q, st["rPose"], True) for q in queue] + [np.asarray(frames[k], np.float32)]
+        queue = queue[-3:]
+        got = odo.ctx.map_records()
+        want = np.concatenate(queue, axis=0)
+        assert np.array_equal(got[:, 0:3], want[:, 0:3]) and np.array_equal(got[:, 4:7], want[:, 4:7])
+        gt = seq.relative_gt(k)
+        assert np.linalg.norm(st["rPose"][:3, 3] - gt[:3, 3]) < 0.05 and _rot_err(st["rPose"][:3, :3], gt[:3, :3]) < 5e-3
+    ref = plo.LaserOdometry(cfg, resident=True, map_mode="reference")          # the reference's live code, queue of 3
+    ref.run(frames)
+    err_c = max(np.linalg.norm(odo.frame_stats[k]["rPose"][:3, 3] - seq.relative_gt(k)[:3, 3]) for k in range(2, 5))
+    err_r = max(np.linalg.norm(ref.frame_stats[k]["rPose"][:3, 3] - seq.relative_gt(k)[:3, 3]) for k in range(2, 5))
+    assert err_c < err_r

@@ -368,3 +368,32 @@ def test_huber_exp_weight_mode_and_solver_dispatch(oracle_mod):
         assert np.linalg.norm(T[:3, 3] - pair.T_gt[:3, 3]) < 0.03, name
     # RANSAC (first hypothesis accepted or not) + Weighted LS final ~ huber_exp WLS at T_best=I
     assert np.abs(res["huber"] - res["unit"]).max() < 5e-3
+
+
+def test_transform_to_end_matches_numpy(oracle_mod):
+    """orc_transform_to_end (TransformToEnd, src/laser_odometry.cpp:88-114): p' = R^T (p - t), n' = R^T n."""
+    rng = np.random.default_rng(31)
+    rec = np.zeros((500, 12), np.float32)
+    rec[:, 0:3] = rng.uniform(-40, 40, size=(500, 3))
+    nrm = rng.normal(size=(500, 3))
+    rec[:, 4:7] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    rec[:, 3] = 7.0
+    a, b, c = 0.03, -0.01, 0.02
+    Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(c), -np.sin(c)], [0, np.sin(c), np.cos(c)]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = [0.7, -0.05, 0.02]
+    out = oracle_mod.transform_to_end(rec, T, True)
+    p = (rec[:, 0:3].astype(np.float64) - T[:3, 3]) @ T[:3, :3]          # rows: R^T (p - t)
+    n = rec[:, 4:7].astype(np.float64) @ T[:3, :3]
+    assert np.abs(out[:, 0:3] - p).max() < 4e-6 and np.abs(out[:, 4:7] - n).max() < 1e-7     # float32 store
+    assert np.array_equal(out[:, 3], rec[:, 3])                                                # other fields untouched
+    keep = oracle_mod.transform_to_end(rec, T, False)
+    assert np.array_equal(keep[:, 4:7], rec[:, 4:7]) and np.array_equal(keep[:, 0:3], out[:, 0:3])
+    # round trip: forward with T, back with T^-1
+    back = oracle_mod.transform_to_end(out, np.linalg.inv(T), True)
+    assert np.abs(back[:, 0:3] - rec[:, 0:3]).max() < 1e-5
+    ident = oracle_mod.transform_to_end(rec, np.eye(4), True)
+    assert np.array_equal(ident, rec)
