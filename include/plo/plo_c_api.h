@@ -261,6 +261,52 @@ PLO_API int plo_map_info(plo_ctx* ctx, int32_t* frames, int64_t* points);
 /* the map as 32-byte records {x,y,z,0,nx,ny,nz,0} (floats), oldest frame first; cap in records */
 PLO_API int plo_map_get(plo_ctx* ctx, float* records8, int64_t cap);
 
+/* ---- front-end normals + presample ------------------------------
+ * The stage of laserCloudHandler (src/scan_registration.cpp) that turns the raw /velodyne_points cloud into
+ * /laser_cloud_filtered — the cloud with normals that plo_set_target / plo_set_source consume — at the
+ * config.json defaults (format "pointcloud", method "pca", neighbor_scan "kdtree", presample
+ * "geometric_features"): range gate (:862-863), ring assignment (:938-1016), intensity = ring + scanPeriod *
+ * relTime (:1018-1042), per-ring clouds (:1043), windowed PCA over three rings (computeNormalPCA :158-229 in the
+ * loop of :1162-1229) with the plane check (:137-156), planarity presample (computeGeometricFeatures :279-327,
+ * :1481-1489).  The sampling stage behind it (:1493 samplePointCloud -> /laser_cloud_flat) is out of scope.
+ * Float32 arithmetic as in the reference; the un-vendored pieces (Eigen reductions / eigen-solver, FLANN ties,
+ * libm overloads) are defined as in oracle/plo_oracle_frontend.c.  The result stays on the device. */
+typedef struct plo_frontend_params {
+  int32_t n_scans;                 /* launch parameter scan_line: 16, 32 or 64                  64 */
+  float min_range, max_range;      /* MINIMUM_RANGE / MAXIMUM_RANGE (:62-63)             0.5 / 120 */
+  float scan_period;               /* :55                                                       0.1 */
+  int32_t window_size, iter_step;  /* compute_normal_method.pca                               3 / 1 */
+  float knn_distance_threshold;    /* pca.knn_distance_threshold (SQUARED metres, as FLANN's)    10 */
+  float plane_distance_threshold;  /* pca.plane_constraint.distance_threshold                  0.02 */
+  float valid_points_threshold;    /* pca.plane_constraint.valid_points_threshold               0.8 */
+  int32_t use_all_points;          /* model.use_all_points                                        1 */
+  float planarity_threshold;       /* presample_method.geometric_features.planarity_threshold  0.05 */
+} plo_frontend_params;
+
+typedef struct plo_frontend_stats {
+  int64_t n_out;           /* points of filteredLaserCloud                                   */
+  int64_t gated;           /* points after removeNaN + range gate                            */
+  int64_t ringed;          /* of those, points with a ring ("points size", :1060)            */
+  int64_t pca_failures;    /* "pca failure points size" (:1228): skipped                     */
+  int64_t plane_failures;  /* "plane check failure points size" (:1229): kept, never presampled */
+  int64_t candidates;      /* "Presampled points size" (:1491)                               */
+} plo_frontend_stats;
+
+PLO_API void plo_frontend_default_params(plo_frontend_params* p);
+/* pts: n records of stride_bytes, float32 xyz at byte 0.  stats (nullable) costs the one synchronisation. */
+PLO_API int plo_frontend(plo_ctx* ctx, const void* host_pts, int64_t n, int32_t stride_bytes, const plo_frontend_params* p,
+                         plo_frontend_stats* stats);
+PLO_API int plo_frontend_device(plo_ctx* ctx, const void* dev_pts, int64_t n, int32_t stride_bytes,
+                                const plo_frontend_params* p, plo_frontend_stats* stats);
+/* results of the last run; every pointer nullable; cap in points.  records12: 48-byte PointXYZINormal records
+ * (x y z 1 | nx ny nz 0 | intensity curvature 0 0); eigenvalues3: l1 >= l2 >= l3 (-1 -1 -1 after a failed plane
+ * check); candidate: planarity presample flag; src_index: index into the input cloud. */
+PLO_API int plo_frontend_get(plo_ctx* ctx, float* records12, float* eigenvalues3, uint8_t* candidate, int32_t* src_index,
+                             int64_t cap);
+/* device pointer to the 48-byte records of the last run and their count (for plo_set_source_device /
+ * plo_set_target_device / plo_map_push_device: the cloud never leaves the GPU); valid until the next run */
+PLO_API int plo_frontend_device_records(plo_ctx* ctx, const void** dev_records, int64_t* n);
+
 /* ---- introspection (bench / tests) ------------------------------------------------ */
 /* kernels launched by this context since creation (bench.py's gpu_launches claim) */
 PLO_API int64_t plo_launch_count(const plo_ctx* ctx);

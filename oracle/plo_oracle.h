@@ -196,4 +196,27 @@ double orc_last_build_seconds(const orc_ctx* c);
 #ifdef __cplusplus
 }
 #endif
+/* ---- front-end: ring assignment + windowed PCA normals + planarity presample ----
+ * laserCloudHandler of src/scan_registration.cpp at config.json defaults; see plo_oracle_frontend.c for
+ * the file:line map and the defined third-party arithmetic. */
+typedef struct orc_frontend_params {
+  int32_t n_scans;               /* 16 / 32 / 64 (launch parameter scan_line) */
+  float min_range, max_range;    /* MINIMUM_RANGE / MAXIMUM_RANGE, src/scan_registration.cpp:62-63 */
+  float scan_period;             /* :55 */
+  int32_t window_size, iter_step;            /* compute_normal_method.pca */
+  float knn_distance_threshold;              /* squared metres (FLANN returns squared distances) */
+  float plane_distance_threshold, valid_points_threshold;   /* pca.plane_constraint */
+  int32_t use_all_points;                    /* model.use_all_points */
+  float planarity_threshold;                 /* presample_method.geometric_features */
+} orc_frontend_params;
+void orc_frontend_default_params(orc_frontend_params* p);
+/* pts: n records of `stride` bytes, float32 xyz at byte 0 (the raw /velodyne_points cloud).
+ * out_records12: filteredLaserCloud as 48-byte PointXYZINormal records (12 floats: x y z 1 | nx ny nz 0 |
+ * intensity curvature 0 0), capacity n; out_eigenvalues: l1 >= l2 >= l3 per output point (-1 -1 -1 for a
+ * failed plane check); out_candidate: planarity presample flag; out_src_index: index into pts.
+ * stats4: points with a ring, PCA failures (skipped), plane-check failures (kept), candidates.
+ * Any output may be NULL.  Returns the number of output points. */
+int64_t orc_frontend(const void* pts, int64_t n, int32_t stride, const orc_frontend_params* P, float* out_records12,
+                     float* out_eigenvalues, uint8_t* out_candidate, int32_t* out_src_index, int64_t* stats4);
+
 #endif

@@ -35,15 +35,21 @@ class OrcParams(C.Structure):
     ]
 
 
+class OrcFrontendParams(C.Structure):
+    _fields_ = [("n_scans", C.c_int32), ("min_range", C.c_float), ("max_range", C.c_float), ("scan_period", C.c_float),
+                ("window_size", C.c_int32), ("iter_step", C.c_int32), ("knn_distance_threshold", C.c_float),
+                ("plane_distance_threshold", C.c_float), ("valid_points_threshold", C.c_float), ("use_all_points", C.c_int32),
+                ("planarity_threshold", C.c_float)]
+
+
 class OrcRegStats(C.Structure):
     _fields_ = [("status", C.c_int32), ("iters", C.c_int32), ("pairs", C.c_int64), ("rms", C.c_double),
                 ("counters", C.c_int64 * 6)]
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(ORACLE_DIR, "plo_oracle.c")
-    hdr = os.path.join(ORACLE_DIR, "plo_oracle.h")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    deps = [os.path.join(ORACLE_DIR, f) for f in ("plo_oracle.c", "plo_oracle_frontend.c", "plo_oracle.h")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "libplo_oracle.so"], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
@@ -229,6 +235,37 @@ def transform_to_end(rec: np.ndarray, T, transform_normal: bool = False) -> np.n
     L.orc_transform_to_end.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int]
     L.orc_transform_to_end(_p(out), out.shape[0], out.strides[0], _p(T), int(bool(transform_normal)))
     return out
+
+
+def frontend_default_params(**over) -> OrcFrontendParams:
+    p = OrcFrontendParams()
+    L = lib()
+    L.orc_frontend_default_params.argtypes = [C.POINTER(OrcFrontendParams)]
+    L.orc_frontend_default_params.restype = None
+    L.orc_frontend_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def frontend(points: np.ndarray, params: OrcFrontendParams | None = None) -> dict:
+    """laserCloudHandler's normal + presample stage (src/scan_registration.cpp) on (n, >=3) float32 points."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n = pts.shape[0]
+    p = params or frontend_default_params()
+    rec = np.zeros((max(n, 1), 12), np.float32)
+    ev = np.zeros((max(n, 1), 3), np.float32)
+    cand = np.zeros(max(n, 1), np.uint8)
+    src = np.zeros(max(n, 1), np.int32)
+    st = np.zeros(4, np.int64)
+    L = lib()
+    L.orc_frontend.restype = C.c_int64
+    L.orc_frontend.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(OrcFrontendParams)] + [C.c_void_p] * 5
+    m = L.orc_frontend(_p(pts), n, pts.strides[0] if n else 12, C.byref(p), _p(rec), _p(ev), _p(cand), _p(src), _p(st))
+    return dict(n=int(m), records=rec[:m], eigenvalues=ev[:m], candidate=cand[:m].astype(bool), src_index=src[:m],
+                ringed=int(st[0]), pca_failures=int(st[1]), plane_failures=int(st[2]), candidates=int(st[3]))
 
 
 def solve_wls(src, ref, nrm, w=None):

@@ -9,12 +9,12 @@ classes without the built library, or without a GPU, fails loudly.
 """
 from . import synth  # noqa: F401
 from . import _lib, config, distributed  # noqa: F401
-from ._lib import PloError, PloParams, default_params  # noqa: F401
+from ._lib import PloError, PloFrontendParams, PloParams, default_params, frontend_default_params  # noqa: F401
 from .context import Context  # noqa: F401
 from .matcher import IMLSICPMatcher  # noqa: F401
 from .odometry import LaserOdometry, save_poses_tum  # noqa: F401
 from .solver import SolveMotionEstimationProblemWeightedLS_CUDA, solveMotionEstimationProblem  # noqa: F401
 
 __all__ = ["synth", "config", "Context", "IMLSICPMatcher", "LaserOdometry", "PloError", "PloParams",
-           "default_params", "SolveMotionEstimationProblemWeightedLS_CUDA", "solveMotionEstimationProblem",
+           "default_params", "frontend_default_params", "PloFrontendParams", "SolveMotionEstimationProblemWeightedLS_CUDA", "solveMotionEstimationProblem",
            "save_poses_tum"]

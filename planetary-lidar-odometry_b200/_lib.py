@@ -53,6 +53,19 @@ class PloRegStats(C.Structure):
                 ("rank", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PloFrontendParams(C.Structure):
+    """plo_frontend_params (include/plo/plo_c_api.h)"""
+    _fields_ = [("n_scans", C.c_int32), ("min_range", C.c_float), ("max_range", C.c_float), ("scan_period", C.c_float),
+                ("window_size", C.c_int32), ("iter_step", C.c_int32), ("knn_distance_threshold", C.c_float),
+                ("plane_distance_threshold", C.c_float), ("valid_points_threshold", C.c_float), ("use_all_points", C.c_int32),
+                ("planarity_threshold", C.c_float)]
+
+
+class PloFrontendStats(C.Structure):
+    _fields_ = [("n_out", C.c_int64), ("gated", C.c_int64), ("ringed", C.c_int64), ("pca_failures", C.c_int64),
+                ("plane_failures", C.c_int64), ("candidates", C.c_int64)]
+
+
 EXPORTS = [
     "plo_create", "plo_destroy", "plo_last_error", "plo_version", "plo_set_stream", "plo_synchronize",
     "plo_default_params", "plo_set_params", "plo_set_target", "plo_set_source", "plo_set_target_device",
@@ -61,6 +74,7 @@ EXPORTS = [
     "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
     "plo_last_kernel_timings", "plo_map_reset", "plo_map_push", "plo_map_push_device", "plo_map_info", "plo_map_get",
+    "plo_frontend_default_params", "plo_frontend", "plo_frontend_device", "plo_frontend_get", "plo_frontend_device_records",
 ]
 
 
@@ -122,8 +136,24 @@ def lib() -> C.CDLL:
     L.plo_map_push_device.argtypes = [vp, vp, i64, i32, vp, i32, i32, i32]
     L.plo_map_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
     L.plo_map_get.argtypes = [vp, vp, i64]
+    L.plo_frontend_default_params.argtypes = [C.POINTER(PloFrontendParams)]
+    L.plo_frontend_default_params.restype = None
+    L.plo_frontend.argtypes = [vp, vp, i64, i32, C.POINTER(PloFrontendParams), C.POINTER(PloFrontendStats)]
+    L.plo_frontend_device.argtypes = [vp, vp, i64, i32, C.POINTER(PloFrontendParams), C.POINTER(PloFrontendStats)]
+    L.plo_frontend_get.argtypes = [vp, vp, vp, vp, vp, i64]
+    L.plo_frontend_device_records.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     _lib = L
     return L
+
+
+def frontend_default_params(**over) -> PloFrontendParams:
+    p = PloFrontendParams()
+    lib().plo_frontend_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"plo_frontend_params has no field {k!r}")
+        setattr(p, k, v)
+    return p
 
 
 def default_params(**over) -> PloParams:

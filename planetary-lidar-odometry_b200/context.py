@@ -101,6 +101,56 @@ class Context:
         self._keep_s = keep
         self._ck((self.L.plo_set_source_device if dev else self.L.plo_set_source)(self.h, p, n, stride))
 
+    # -- front-end (plo_frontend*) ----------------------------------------------------------
+    def frontend(self, points, params=None, fetch: bool = True):
+        """laserCloudHandler's normal + presample stage (src/scan_registration.cpp) on raw points: numpy (n, >=3)
+        float32, or a CUDA tensor.  The filtered cloud stays on the device (frontend_device_records); with `fetch`
+        it is also returned: records (n_out, 12), eigenvalues, candidate flags, src_index."""
+        fp = params or _lib.frontend_default_params()
+        st = _lib.PloFrontendStats()
+        if _is_torch_cuda(points):
+            t = points.contiguous()
+            self._keep_fe = t
+            n, stride = int(t.shape[0]), int(t.stride(0) * t.element_size()) if t.shape[0] else 12
+            self._ck(self.L.plo_frontend_device(self.h, C.c_void_p(t.data_ptr()), n, stride, C.byref(fp), C.byref(st)))
+        else:
+            a = np.ascontiguousarray(points, dtype=np.float32)
+            n, stride = a.shape[0], (a.strides[0] if a.shape[0] else 12)
+            self._ck(self.L.plo_frontend(self.h, _ptr(a), n, stride, C.byref(fp), C.byref(st)))
+        out = dict(n=int(st.n_out), gated=int(st.gated), ringed=int(st.ringed), pca_failures=int(st.pca_failures),
+                   plane_failures=int(st.plane_failures), candidates=int(st.candidates))
+        if fetch:
+            m = max(out["n"], 1)
+            rec = np.zeros((m, 12), np.float32)
+            ev = np.zeros((m, 3), np.float32)
+            cand = np.zeros(m, np.uint8)
+            src = np.zeros(m, np.int32)
+            self._ck(self.L.plo_frontend_get(self.h, _ptr(rec), _ptr(ev), _ptr(cand), _ptr(src), m))
+            k = out["n"]
+            out.update(records=rec[:k], eigenvalues=ev[:k], candidate=cand[:k].astype(bool), src_index=src[:k])
+        return out
+
+    def frontend_device_records(self):
+        """(device pointer, n) of the 48-byte records of the last frontend() run"""
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.L.plo_frontend_device_records(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_source_from_frontend(self):
+        p, n = self.frontend_device_records()
+        self._ck(self.L.plo_set_source_device(self.h, C.c_void_p(p), n, 48))
+
+    def set_target_from_frontend(self):
+        p, n = self.frontend_device_records()
+        self._ck(self.L.plo_set_target_device(self.h, C.c_void_p(p), n, 48))
+
+    def map_push_from_frontend(self, T_last_curr=None, from_last_register: bool = False, max_queue: int = 1,
+                               transform_normals: bool = False):
+        p, n = self.frontend_device_records()
+        T = None if T_last_curr is None else np.ascontiguousarray(T_last_curr, dtype=np.float64).reshape(16)
+        self._ck(self.L.plo_map_push_device(self.h, C.c_void_p(p), n, 48, _ptr(T), 1 if from_last_register else 0,
+                                            int(max_queue), 1 if transform_normals else 0))
+
     # -- device-resident local map (plo_map_*) -------------------------------------------
     def map_reset(self):
         self._ck(self.L.plo_map_reset(self.h))

@@ -179,7 +179,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
@@ -334,6 +334,88 @@ int plo_map_get(plo_ctx* c, float* records8, int64_t cap) {
   PLO_CUDA(c, cudaSetDevice(c->device));
   PLO_CUDA(c, cudaMemcpyAsync(records8, c->map_rec[c->map_cur].p, sizeof(float) * 8 * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
   PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+void plo_frontend_default_params(plo_frontend_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->n_scans = 64;
+  p->min_range = 0.5f;                 // src/scan_registration.cpp:62
+  p->max_range = 120.0f;               // :63
+  p->scan_period = 0.1f;               // :55
+  p->window_size = 3;                  // config.json:9
+  p->iter_step = 1;                    // :10
+  p->knn_distance_threshold = 10.0f;   // :11
+  p->plane_distance_threshold = 0.02f; // :14
+  p->valid_points_threshold = 0.8f;    // :15
+  p->use_all_points = 1;               // :78
+  p->planarity_threshold = 0.05f;      // :39
+}
+
+static int frontend_common(plo_ctx* c, const void* dev_pts, int64_t n, int32_t stride, const plo_frontend_params* p,
+                           plo_frontend_stats* stats) {
+  if (!p) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend: params is NULL");
+  if (p->n_scans != 16 && p->n_scans != 32 && p->n_scans != 64)
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend: n_scans must be 16, 32 or 64 (\"wrong scan number\", scan_registration.cpp:1011)");
+  if (p->window_size < 0 || p->iter_step < 1 || (2 * p->window_size) / p->iter_step + 1 > 64)
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend: bad window_size / iter_step");
+  PLO_TRY(plo_frontend_run(c, dev_pts, n, stride, p));
+  if (stats) {
+    int64_t v[7];
+    PLO_TRY(plo_frontend_fetch_counts(c, v));
+    stats->n_out = v[0]; stats->gated = v[1]; stats->ringed = v[2];
+    stats->pca_failures = v[3]; stats->plane_failures = v[4]; stats->candidates = v[5];
+  }
+  return PLO_OK;
+}
+
+int plo_frontend(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride, const plo_frontend_params* p, plo_frontend_stats* stats) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !host_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend: bad pointer / count");
+  if (stride < 12 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend: stride must be >= 12 and a multiple of 4");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  if (n > 0) {
+    PLO_CUDA(c, c->fe_stage.reserve((size_t)n * stride));
+    PLO_CUDA(c, cudaMemcpyAsync(c->fe_stage.p, host_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+  }
+  return frontend_common(c, c->fe_stage.p, n, stride, p, stats);
+}
+
+int plo_frontend_device(plo_ctx* c, const void* dev_pts, int64_t n, int32_t stride, const plo_frontend_params* p,
+                        plo_frontend_stats* stats) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !dev_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend_device: bad pointer / count");
+  if (stride < 12 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend_device: bad stride");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  return frontend_common(c, dev_pts, n, stride, p, stats);
+}
+
+int plo_frontend_get(plo_ctx* c, float* records12, float* eigenvalues3, uint8_t* candidate, int32_t* src_index, int64_t cap) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (!c->fe_valid) return plo_fail(c, PLO_ERR_STATE, "plo_frontend_get: call plo_frontend first");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  int64_t v[7];
+  PLO_TRY(plo_frontend_fetch_counts(c, v));
+  const size_t m = (size_t)v[0];
+  if ((int64_t)m > cap) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend_get: buffers too small");
+  if (m == 0) return PLO_OK;
+  if (records12) PLO_CUDA(c, cudaMemcpyAsync(records12, c->fe_rec.p, sizeof(float) * 12 * m, cudaMemcpyDeviceToHost, c->stream));
+  if (eigenvalues3) PLO_CUDA(c, cudaMemcpyAsync(eigenvalues3, c->fe_ev3.p, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
+  if (candidate) PLO_CUDA(c, cudaMemcpyAsync(candidate, c->fe_cand.p, m, cudaMemcpyDeviceToHost, c->stream));
+  if (src_index) PLO_CUDA(c, cudaMemcpyAsync(src_index, c->fe_src.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int plo_frontend_device_records(plo_ctx* c, const void** dev_records, int64_t* n) {
+  if (!c || !dev_records || !n) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_frontend_device_records: NULL argument");
+  if (!c->fe_valid) return plo_fail(c, PLO_ERR_STATE, "plo_frontend_device_records: call plo_frontend first");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  int64_t v[7];
+  PLO_TRY(plo_frontend_fetch_counts(c, v));
+  *dev_records = c->fe_rec.p;
+  *n = v[0];
   return PLO_OK;
 }
 

@@ -143,6 +143,12 @@ struct plo_ctx {
   int map_cur = 0;
   std::vector<int64_t> map_frames;   // points per queued frame, oldest first
 
+  // front-end (plo_frontend): scratch and the filtered cloud of the last run, device-resident
+  DevBuf fe_stage, fe_counts, fe_blockcnt, fe_kp, fe_ring, fe_inten, fe_rp, fe_rsrc, fe_nn[2], fe_status, fe_nrm, fe_ev;
+  DevBuf fe_rec, fe_ev3, fe_cand, fe_src, fe_keys[2], fe_vals[2], fe_hist, fe_tot;
+  int64_t fe_n_in = 0;
+  bool fe_valid = false;
+
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
   bool prev_valid = false;   // q_x / q_kd2 hold the previous projection of the SAME clouds and k, r
@@ -204,6 +210,9 @@ size_t plo_sort_hist_ints(int64_t n);
 size_t plo_sort_total_ints(int passes);
 int plo_map_push_records(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const double* T_host_or_null,
                          bool pose_from_device, int32_t max_queue, bool transform_normals);
+// ---- frontend.cu ------------------------------------------------------------------
+int plo_frontend_run(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const plo_frontend_params* fp);
+int plo_frontend_fetch_counts(plo_ctx* c, int64_t out7[7]);
 // ---- knn_project.cu ---------------------------------------------------------------
 int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);

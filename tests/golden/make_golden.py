@@ -62,7 +62,41 @@ def projection_block(tgt, src, T, **kw):
     return o, out
 
 
+def frontend_case():
+    """Front-end golden: a 70-degree sector of the VLP-16 planetary scan (seed 3001)."""
+    pair = W.planetary_pair()
+    pts = np.ascontiguousarray(pair.source[:, 0:3])
+    az = np.degrees(np.arctan2(pts[:, 1], pts[:, 0]))
+    pts = np.ascontiguousarray(pts[(az > -35) & (az < 35)])
+    kw = dict(n_scans=16, plane_distance_threshold=0.05)
+    r = orc.frontend(pts, orc.frontend_default_params(**kw))
+    # independent check of the normals: float64 eigh of the 21-row windows rebuilt from ring ids in numpy
+    ang = np.degrees(np.arctan(pts[:, 2] / np.hypot(pts[:, 0], pts[:, 1])))
+    rid = np.floor((ang + 15) / 2 + 0.5).astype(int)
+    ok = np.nonzero(r["eigenvalues"][:, 0] > 0)[0]
+    for k in ok[:: max(1, len(ok) // 50)]:
+        q = r["records"][k, 0:3]
+        i = rid[r["src_index"][k]]
+        own = pts[rid == i]
+        j = int(np.nonzero((own == q).all(axis=1))[0][0])
+        rows = [own[j - 3:j + 4]]
+        for nbr in (i - 1, i + 1):
+            cl = pts[rid == nbr]
+            nn = int(np.argmin(((cl - q) ** 2).sum(axis=1)))
+            rows.append(cl[nn - 3:nn + 4])
+        P = np.concatenate(rows).astype(np.float64)
+        assert P.shape == (21, 3)
+        w, V = np.linalg.eigh(np.cov(P.T))
+        assert abs(abs(V[:, 0] @ r["records"][k, 4:7]) - 1) < 1e-4 and np.allclose(w[::-1], r["eigenvalues"][k], rtol=5e-3, atol=1e-7)
+    out = os.path.join(HERE, "frontend_vlp16.npz")
+    np.savez_compressed(out, points=pts, n_scans=16, plane_distance_threshold=0.05, records=r["records"],
+                        eigenvalues=r["eigenvalues"], candidate=r["candidate"], src_index=r["src_index"],
+                        stats=np.array([r["n"], r["ringed"], r["pca_failures"], r["plane_failures"], r["candidates"]], np.int64))
+    print("frontend_vlp16 points", pts.shape[0], "->", r["n"], "candidates", r["candidates"], os.path.getsize(out) // 1024, "KiB")
+
+
 def main():
+    frontend_case()
     for name, maker, kw in (("urban_hdl64", case_urban, {}), ("planetary_vlp16", case_planetary, dict(h=2.0, r=6.0))):
         tgt, src, T_gt = maker()
         o, pr = projection_block(tgt, src, np.eye(4), **kw)

@@ -111,3 +111,28 @@ def test_cuda_path_reproduces_golden(name):
     got = {**ctx.neighbors(), **ctx.query_results()}
     assert np.array_equal(got["nn_idx"], g["gt_nn_idx"]) and np.array_equal(got["status"], g["gt_status"])
     assert np.array_equal(pg["counters"], g["gt_counters"])
+
+
+def _frontend_golden():
+    g = _load("frontend_vlp16")
+    return g, dict(n_scans=int(g["n_scans"]), plane_distance_threshold=float(g["plane_distance_threshold"]))
+
+
+def test_frontend_oracle_reproduces_golden(oracle_mod):
+    g, kw = _frontend_golden()
+    r = oracle_mod.frontend(g["points"], oracle_mod.frontend_default_params(**kw))
+    assert [r["n"], r["ringed"], r["pca_failures"], r["plane_failures"], r["candidates"]] == list(g["stats"])
+    assert np.array_equal(r["src_index"], g["src_index"]) and np.array_equal(r["candidate"], g["candidate"])
+    assert np.array_equal(r["records"][:, 0:8], g["records"][:, 0:8]) and np.array_equal(r["eigenvalues"], g["eigenvalues"])
+    assert np.abs(r["records"][:, 8] - g["records"][:, 8]).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_frontend_cuda_reproduces_golden():
+    import plo_b200 as plo
+    g, kw = _frontend_golden()
+    r = plo.Context(0).frontend(g["points"], plo.frontend_default_params(**kw))
+    assert [r["n"], r["ringed"], r["pca_failures"], r["plane_failures"], r["candidates"]] == list(g["stats"])
+    assert np.array_equal(r["src_index"], g["src_index"]) and np.array_equal(r["candidate"], g["candidate"])
+    assert np.array_equal(r["records"][:, 0:8], g["records"][:, 0:8]) and np.array_equal(r["eigenvalues"], g["eigenvalues"])
+    assert np.abs(r["records"][:, 8] - g["records"][:, 8]).max() <= 1e-6

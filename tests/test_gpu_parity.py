@@ -754,3 +754,71 @@ def test_consistent_local_map_odometry(oracle_mod):
     err_c = max(np.linalg.norm(odo.frame_stats[k]["rPose"][:3, 3] - seq.relative_gt(k)[:3, 3]) for k in range(2, 5))
     err_r = max(np.linalg.norm(ref.frame_stats[k]["rPose"][:3, 3] - seq.relative_gt(k)[:3, 3]) for k in range(2, 5))
     assert err_c < err_r
+
+
+def _check_frontend(oracle_mod, ctx, pts, **kw):
+    g = ctx.frontend(pts, plo.frontend_default_params(**kw))
+    o = oracle_mod.frontend(pts, oracle_mod.frontend_default_params(**kw))
+    for key in ("n", "ringed", "pca_failures", "plane_failures", "candidates"):
+        assert g[key] == o[key], (key, g[key], o[key])
+    assert np.array_equal(g["src_index"], o["src_index"])
+    assert np.array_equal(g["candidate"], o["candidate"])
+    gr, orr = g["records"], o["records"]
+    assert np.array_equal(gr[:, 0:4], orr[:, 0:4])                       # xyz + the constant 1
+    assert np.array_equal(gr[:, 4:8], orr[:, 4:8])                       # normals: same float statements on both sides
+    assert np.array_equal(g["eigenvalues"], o["eigenvalues"])
+    assert np.abs(gr[:, 8] - orr[:, 8]).max() <= 1e-6 if g["n"] else True   # intensity goes through atan2 (libm vs CUDA)
+    assert np.array_equal(gr[:, 9:12], orr[:, 9:12])
+    return g, o
+
+
+def test_frontend_normals_and_presample(oracle_mod):
+    """SURVEY.md §8f rank 3 — the front-end stage that produces the normals the matcher consumes
+    (src/scan_registration.cpp: ring assignment, windowed PCA over three rings, plane check, planarity presample)
+    against the oracle's restatement: identical point selection and order, identical normals / eigenvalues /
+    presample flags; intensity (scanID + scanPeriod * relTime) within 1e-6."""
+    ctx = plo.Context(0)
+    pair = W.hdl64_pair()
+    pts = np.ascontiguousarray(pair.source[:, 0:3])
+    g, o = _check_frontend(oracle_mod, ctx, pts)
+    assert g["n"] > 80000 and g["candidates"] > 10000
+    # the computed normals agree with the analytic surface normals of the synthetic scene where the plane check held
+    ok = g["eigenvalues"][:, 0] > 0
+    cosang = np.abs((pair.source[g["src_index"], 4:7] * g["records"][:, 4:7]).sum(axis=1))
+    assert np.median(cosang[ok]) > 0.999
+    # other ring layouts, windows, thresholds; NaNs, points out of range; use_all_points off
+    bad = pts.copy()
+    bad[::97, 1] = np.nan
+    bad[5::131] *= 100.0
+    bad[7::211] *= 0.001
+    _check_frontend(oracle_mod, ctx, bad, use_all_points=0, window_size=2, plane_distance_threshold=0.05)
+    _check_frontend(oracle_mod, ctx, pts, window_size=4, iter_step=2, knn_distance_threshold=0.5, planarity_threshold=0.2)
+    seq = W.Sequence(seed=2001, n_frames=1)                                   # VLP-32C-shaped
+    _check_frontend(oracle_mod, ctx, np.ascontiguousarray(seq.frame(0)[:, 0:3]), n_scans=32)
+    pl = W.planetary_pair()                                                   # VLP-16
+    _check_frontend(oracle_mod, ctx, np.ascontiguousarray(pl.source[:, 0:3]), n_scans=16, plane_distance_threshold=0.05)
+    # degenerate inputs
+    _check_frontend(oracle_mod, ctx, pts[:0])
+    _check_frontend(oracle_mod, ctx, pts[:10])
+    _check_frontend(oracle_mod, ctx, np.full((50, 3), np.nan, np.float32))
+
+
+def test_frontend_feeds_the_matcher_on_the_device(oracle_mod):
+    """raw scans -> plo_frontend -> plo_set_target_device / plo_set_source_device -> plo_register, the filtered
+    clouds never leaving the GPU; same result as handing the oracle front-end's clouds to the oracle matcher."""
+    pair = W.hdl64_pair()
+    a = np.ascontiguousarray(pair.target[::2, 0:3])
+    b = np.ascontiguousarray(pair.source[::2, 0:3])
+    ctx = plo.Context(0)
+    ctx.frontend(a, fetch=False)
+    ctx.set_target_from_frontend()
+    ctx.frontend(b, fetch=False)
+    ctx.set_source_from_frontend()
+    Tg, sg = ctx.register()
+    orc = oracle_mod.Oracle()
+    orc.set_target(oracle_mod.frontend(a)["records"])
+    orc.set_source(oracle_mod.frontend(b)["records"])
+    To, so = orc.register()
+    assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    assert np.linalg.norm(Tg[:3, 3] - pair.T_gt[:3, 3]) < 0.1

@@ -397,3 +397,56 @@ def test_transform_to_end_matches_numpy(oracle_mod):
     assert np.abs(back[:, 0:3] - rec[:, 0:3]).max() < 1e-5
     ident = oracle_mod.transform_to_end(rec, np.eye(4), True)
     assert np.array_equal(ident, rec)
+
+
+def test_frontend_oracle_properties(oracle_mod):
+    """oracle/plo_oracle_frontend.c (src/scan_registration.cpp front-end): selection rules, order, and one PCA window
+    re-done in numpy."""
+    import plo_b200 as plo
+    pair = plo.synth.workloads.planetary_pair()                        # VLP-16: small enough for the CPU suite
+    pts = np.ascontiguousarray(pair.source[:, 0:3])
+    r = oracle_mod.frontend(pts, oracle_mod.frontend_default_params(n_scans=16, plane_distance_threshold=0.05))
+    assert 0 < r["n"] <= r["ringed"] <= pts.shape[0]
+    rec = r["records"]
+    assert np.array_equal(rec[:, 0:3], pts[r["src_index"]])            # points are copied, never altered
+    assert np.allclose(np.linalg.norm(rec[:, 4:7], axis=1), 1.0, atol=1e-6) and (rec[:, 6] >= 0).all()   # unit, +z
+    ring = np.floor(rec[:, 8]).astype(int)                             # intensity = ring + 0.1 * relTime
+    assert (np.diff(ring) >= 0).all() and ring.min() >= 1 and ring.max() <= 14     # ring-major, rings 1 .. N-2 only
+    assert ((rec[:, 8] - ring) >= 0).all() and ((rec[:, 8] - ring) < 0.2).all()      # relTime of a ring-major synthetic scan
+    ev = r["eigenvalues"]
+    okp = ev[:, 0] > 0
+    assert (ev[okp, 0] >= ev[okp, 1]).all() and (ev[okp, 1] >= ev[okp, 2] - 1e-9).all()
+    assert np.array_equal(ev[~okp], np.full(((~okp).sum(), 3), -1.0, np.float32)) and (~okp).sum() == r["plane_failures"]
+    plan = (ev[:, 1] - ev[:, 2]) / ev[:, 0]
+    assert np.array_equal(r["candidate"], okp & (plan > 0.05)) and r["candidate"].sum() == r["candidates"]
+    # analytic normals of the synthetic terrain agree where the plane check held
+    cosang = np.abs((pair.source[r["src_index"], 4:7] * rec[:, 4:7]).sum(axis=1))
+    assert np.median(cosang[okp]) > 0.99
+    # one window re-done in numpy (float64 eigh): the 21 rows are the +-3 neighbours on the ring and around the
+    # nearest points of the two adjacent rings
+    ang = np.degrees(np.arctan(pts[:, 2] / np.hypot(pts[:, 0], pts[:, 1])))
+    rid = np.floor((ang + 15) / 2 + 0.5).astype(int)
+    k = int(np.nonzero(okp)[0][len(np.nonzero(okp)[0]) // 2])
+    i = ring[k]
+    rows = []
+    own = pts[rid == i]
+    j = int(np.nonzero((own == rec[k, 0:3]).all(axis=1))[0][0])
+    rows.append(own[j - 3:j + 4])
+    for nbr in (i - 1, i + 1):
+        cl = pts[rid == nbr]
+        nn = int(np.argmin(((cl - rec[k, 0:3]) ** 2).sum(axis=1)))
+        rows.append(cl[nn - 3:nn + 4])
+    P = np.concatenate(rows).astype(np.float64)
+    assert P.shape == (21, 3)
+    C = np.cov(P.T)
+    w, V = np.linalg.eigh(C)
+    n = V[:, 0] if V[2, 0] >= 0 else -V[:, 0]
+    assert abs(abs(n @ rec[k, 4:7]) - 1) < 1e-4 and np.allclose(w[::-1], ev[k], rtol=2e-3, atol=1e-7)
+    # HDL-64: rings above 50 are dropped (:1003), NaN / out-of-range points never reach a ring
+    hd = plo.synth.workloads.hdl64_pair(azimuth_steps=500)
+    q = np.ascontiguousarray(hd.source[:, 0:3]).copy()
+    q[::50, 0] = np.nan
+    q[3::70] *= 500.0
+    r64 = oracle_mod.frontend(q)
+    assert r64["ringed"] < np.isfinite(q).all(axis=1).sum() and np.isfinite(r64["records"]).all()
+    assert oracle_mod.frontend(q[:0])["n"] == 0
