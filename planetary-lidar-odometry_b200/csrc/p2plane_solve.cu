@@ -188,8 +188,9 @@ __device__ void polar_orthogonalize(double R[9]) {
 // diagonally pivoted LDL^T solve of H x = g; returns the number of pivots used.
 // A pivot is dropped when the remaining diagonal is below (max|H_jj| * eps^2) * (cnt-k)/cnt,
 // the squared form of Eigen's ColPivHouseholderQR threshold_helper test (H_jj = |col j|^2).
-// (kept out of line: inlined into k_solve_update, nvcc 12.9 let the caller's x[] share a stack slot with A[][])
-__device__ __noinline__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
+// x must NOT live on the caller's stack: inlined into k_solve_update, nvcc 12.9 let a local x[] share a stack slot
+// with A[][] (wrong results); the callers pass a shared-memory array.
+__device__ __forceinline__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
   double A[6][6];
   int t = 0;
   for (int p = 0; p < 6; ++p)
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__
     for (int i = 0; i < 6; ++i) st->ev[i] = ev[i];
     return;
   }
-  double x[6];
+  __shared__ double x[6];   // see solve_ldlt6
   const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
   if (stage == 1) {
     st->rank = rank;
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(64) k_drpm_finish(const double* __restrict__ p
     st->probs[k] = pr;
     if (pr < minp) minp = pr;
   }
-  double x[6];
+  __shared__ double x[6];   // see solve_ldlt6
   int rank = 6;
   if (minp < P.drpm_threshold) {   // SolveWithSnrProbabilities, include/degeneracy.h:107-131
     double tt[6];
