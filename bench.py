@@ -65,22 +65,51 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
-    def _run(self):
+    def _sample_nvml(self, nv, h):
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((float(sm), float(mx)))
+        for nme, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(nme)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+        f = [x.strip() for x in out.split(",")]
+        self.samples.append((float(f[0]), float(f[1])))
+        for nme, v in zip(names, f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nme)
+
+    def _run(self):
+        # in-process NVML when available: spawning nvidia-smi from every rank stalls kernel launches on a busy node
+        nv = h = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:    # the CUDA ordinal need not be the NVML index (CUDA_VISIBLE_DEVICES): go through the PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(self.index)
+                h = nv.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            nv = None
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append((float(f[0]), float(f[1])))
-                for nme, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nme)
+                if nv is not None:
+                    self._sample_nvml(nv, h)
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if nv is not None else 0.25)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -132,6 +161,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly ONE JSON line: everything else that lands on fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr, and the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -157,7 +194,7 @@ def main():
                              "sample": f"{steps} full registrations (kd-tree build + {st['iters']} ICP iterations each)", **detail},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -175,7 +212,9 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
-    pair = workload(1002 + rank, args.map_points)       # each rank registers its own frame (weak scaling)
+    # weak scaling: every rank registers its own copy of the same frame pair, so that per-GPU work is exactly fixed
+    # as N grows (different scenes would make max-over-ranks measure the hardest scene, not the system)
+    pair = workload(1002, args.map_points)
     n_t, n_s = int(pair.target.shape[0]), int(pair.source.shape[0])
 
     stream = torch.cuda.Stream(device=dev)
@@ -206,7 +245,7 @@ def main():
     for _ in range(args.warmup):
         Tw, sw_ = step_device()
     if world > 1 and args.warmup > 0:      # warm the communicator the end-of-run gather uses
-        plo.distributed.gather_results(plo.distributed.pack_result(Tw, sw_)[None, :], [rank], world, device=dev)
+        plo.distributed.gather_results(plo.distributed.pack_result(Tw, sw_)[None, :], [rank], world, device=dev, slots=1)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     idx_ms, reg_ms = [], []
@@ -243,7 +282,7 @@ def main():
         # the path's only exchange: poses + stats of every rank's units, once per run
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        table = plo.distributed.gather_results(plo.distributed.pack_result(T, st)[None, :], [rank], world, device=dev)
+        table = plo.distributed.gather_results(plo.distributed.pack_result(T, st)[None, :], [rank], world, device=dev, slots=1)
         g1.record()
         torch.cuda.synchronize(dev)
         gather_ms = g0.elapsed_time(g1)
@@ -349,7 +388,7 @@ def main():
         "clocks": clocks.summary(),
         "parity": parity,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -24,9 +24,10 @@ def pack_result(T: np.ndarray, stats: dict | None) -> np.ndarray:
     return row
 
 
-def gather_results(local_rows: np.ndarray, local_units: list[int], n_units: int, device=None):
+def gather_results(local_rows: np.ndarray, local_units: list[int], n_units: int, device=None, slots: int | None = None):
     """All-gather [units_local x RESULT_WIDTH] fp64 blocks and place them by unit id.
-    Returns the [n_units x RESULT_WIDTH] table on every rank."""
+    Returns the [n_units x RESULT_WIDTH] table on every rank.  `slots`: rows reserved per rank when the caller
+    knows the largest shard (skips the sizing all-reduce: ONE collective in total)."""
     import torch
     import torch.distributed as dist
 
@@ -36,9 +37,12 @@ def gather_results(local_rows: np.ndarray, local_units: list[int], n_units: int,
         table[local_units] = local_rows
         return table
     # shards may be ragged (sequences of different lengths): size the slots by the largest one
-    cnt = torch.tensor([len(local_units)], dtype=torch.int64, device=device)
-    dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
-    per = max(int(cnt.item()), 1)
+    if slots is None:
+        cnt = torch.tensor([len(local_units)], dtype=torch.int64, device=device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+        per = max(int(cnt.item()), 1)
+    else:
+        per = max(int(slots), len(local_units), 1)
     buf = torch.zeros((per, RESULT_WIDTH + 1), dtype=torch.float64, device=device)
     if len(local_units):
         buf[:len(local_units), :RESULT_WIDTH] = torch.as_tensor(np.asarray(local_rows), dtype=torch.float64, device=device)
