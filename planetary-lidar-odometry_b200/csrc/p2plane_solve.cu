@@ -327,16 +327,37 @@ __device__ __noinline__ void colpiv_qr_solve_3x6(double A[3][6], double b[3], do
   for (int i = 0; i < nonzero_pivots; ++i) x[perm[i]] = y[i];
 }
 
-// cyclic Jacobi on a symmetric 6 x 6: eigenvalues ascending, eigenvectors in columns (the ordering
-// contract of Eigen::SelfAdjointEigenSolver, src/solver.cpp:540-542)
-__device__ __noinline__ void sym_eigen6(const double Ain[36], double ev[6], double U[36]) {
-  double A[36], V[36];
-  for (int i = 0; i < 36; ++i) { A[i] = Ain[i]; V[i] = (i % 7 == 0) ? 1.0 : 0.0; }
+// DRPM, src/solver.cpp:537-542: eigen-decomposition of the weight-normalised information matrix — cyclic Jacobi
+// on a symmetric 6 x 6, eigenvalues ascending, eigenvectors in columns (the ordering contract of
+// Eigen::SelfAdjointEigenSolver).  One warp: the rotation order is the serial row-cyclic one and every element
+// update is the same single expression as in the oracle's sym_eigen_n (bit-identical results), but the six
+// independent updates of each of a rotation's three loops run on six lanes and the matrices sit in shared memory
+// (the one-thread version cost 0.75 ms per ICP iteration).
+__global__ void __launch_bounds__(32) k_drpm_eigen(DevState* __restrict__ st, DevParams P, int advance_loop) {
+  if (advance_loop && st->done) return;
+  __shared__ double A[36], V[36];
+  const int lane = threadIdx.x;
+  {
+    const double sw = st->sw;
+    const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;   // as k_solve_update
+    if (lane == 0) {
+      int t = 0;
+      for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) { const double h = st->H[t] * scale; A[a * 6 + b] = h; A[b * 6 + a] = h; ++t; }
+    }
+    for (int i = lane; i < 36; i += 32) V[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  }
+  __syncwarp();
   for (int sweep = 0; sweep < 64; ++sweep) {
     double off = 0.0;
     for (int i = 0; i < 6; ++i)
       for (int j = i + 1; j < 6; ++j) off += A[i * 6 + j] * A[i * 6 + j];
-    if (off == 0.0) break;
+    if (off == 0.0) break;   // warp-uniform: every lane read the same values
+    {   // the rotated entry is not zeroed, so `off` bottoms out at rounding noise: same early stop as the oracle
+      double dsum = 0.0;
+      for (int i = 0; i < 6; ++i) dsum += A[i * 7] * A[i * 7];
+      if (off <= 1e-30 * dsum) break;
+    }
     for (int pp = 0; pp < 6; ++pp)
       for (int q = pp + 1; q < 6; ++q) {
         const double apq = A[pp * 6 + q];
@@ -344,18 +365,37 @@ __device__ __noinline__ void sym_eigen6(const double Ain[36], double ev[6], doub
         const double theta = (A[q * 6 + q] - A[pp * 6 + pp]) / (2.0 * apq);
         const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
-        for (int k = 0; k < 6; ++k) { const double akp = A[k * 6 + pp], akq = A[k * 6 + q]; A[k * 6 + pp] = cs * akp - sn * akq; A[k * 6 + q] = sn * akp + cs * akq; }
-        for (int k = 0; k < 6; ++k) { const double apk = A[pp * 6 + k], aqk = A[q * 6 + k]; A[pp * 6 + k] = cs * apk - sn * aqk; A[q * 6 + k] = sn * apk + cs * aqk; }
-        for (int k = 0; k < 6; ++k) { const double vkp = V[k * 6 + pp], vkq = V[k * 6 + q]; V[k * 6 + pp] = cs * vkp - sn * vkq; V[k * 6 + q] = sn * vkp + cs * vkq; }
+        __syncwarp();
+        if (lane < 6) {
+          const int k = lane;
+          const double akp = A[k * 6 + pp], akq = A[k * 6 + q];
+          A[k * 6 + pp] = cs * akp - sn * akq;
+          A[k * 6 + q] = sn * akp + cs * akq;
+        } else if (lane >= 8 && lane < 14) {
+          const int k = lane - 8;
+          const double vkp = V[k * 6 + pp], vkq = V[k * 6 + q];
+          V[k * 6 + pp] = cs * vkp - sn * vkq;
+          V[k * 6 + q] = sn * vkp + cs * vkq;
+        }
+        __syncwarp();
+        if (lane < 6) {
+          const int k = lane;
+          const double apk = A[pp * 6 + k], aqk = A[q * 6 + k];
+          A[pp * 6 + k] = cs * apk - sn * aqk;
+          A[q * 6 + k] = sn * apk + cs * aqk;
+        }
+        __syncwarp();
       }
   }
-  int order[6] = {0, 1, 2, 3, 4, 5};
-  for (int i = 0; i < 6; ++i)
-    for (int j = i + 1; j < 6; ++j)
-      if (A[order[j] * 7] < A[order[i] * 7]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-  for (int i = 0; i < 6; ++i) {
-    ev[i] = A[order[i] * 7];
-    for (int k = 0; k < 6; ++k) U[k * 6 + i] = V[k * 6 + order[i]];
+  if (lane == 0) {
+    int order[6] = {0, 1, 2, 3, 4, 5};
+    for (int i = 0; i < 6; ++i)
+      for (int j = i + 1; j < 6; ++j)
+        if (A[order[j] * 7] < A[order[i] * 7]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+    for (int i = 0; i < 6; ++i) {
+      st->ev[i] = A[order[i] * 7];
+      for (int k = 0; k < 6; ++k) st->U[k * 6 + i] = V[k * 6 + order[i]];
+    }
   }
 }
 
@@ -448,17 +488,7 @@ __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__
   const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
   for (int i = 0; i < 21; ++i) H[i] = s_sum[i] * scale;
   for (int i = 0; i < 6; ++i) g[i] = s_sum[21 + i] * scale;
-  if (stage == 3) {   // DRPM: eigenvectors of the normalised information matrix (src/solver.cpp:537-542)
-    double Hf[36];
-    int t = 0;
-    for (int a = 0; a < 6; ++a)
-      for (int b = a; b < 6; ++b) { Hf[a * 6 + b] = H[t]; Hf[b * 6 + a] = H[t]; ++t; }
-    double ev[6], U[36];
-    sym_eigen6(Hf, ev, U);
-    for (int i = 0; i < 36; ++i) st->U[i] = U[i];
-    for (int i = 0; i < 6; ++i) st->ev[i] = ev[i];
-    return;
-  }
+  if (stage == 3) return;   // DRPM: the sums are in the state; k_drpm_eigen / k_drpm_noise / k_drpm_finish go on
   __shared__ double x[6];   // see solve_ldlt6
   const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
   if (stage == 1) {
@@ -980,6 +1010,9 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   if (drpm) {
+    k_drpm_eigen<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), P, adv);
+    c->launches++;
+    PLO_CUDA(c, cudaGetLastError());
     k_drpm_noise<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                       c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
                                                       c->partials2.as<double>(), adv);
