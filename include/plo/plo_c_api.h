@@ -319,6 +319,9 @@ PLO_API int plo_last_timings(plo_ctx* ctx, float* ms_index_build, float* ms_regi
  * that did work in the last plo_register and how many those were. */
 PLO_API int plo_set_profiling(plo_ctx* ctx, int32_t enabled);
 PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_t* n_project);
+/* the same launches one by one (ICP iteration i of the last plo_register -> ms_each[i], at most cap
+ * and at most 64 entries): shows how the projection gets cheaper as the pose settles */
+PLO_API int plo_last_project_times(plo_ctx* ctx, float* ms_each, int32_t cap, int32_t* n_project);
 /* per-kernel timing of one projection pass for the roofline: runs the projection kernel
  * `reps` times at the current pose and returns the mean device ms per launch */
 PLO_API int plo_time_project_kernel(plo_ctx* ctx, const double T[16], int32_t reps, float* ms_mean);

@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libplo_cuda.so")
+# PLO_LIB: another build of the SAME library (tuning variants from tools/build_variants.sh); never a different backend
+LIB_PATH = os.environ.get("PLO_LIB") or os.path.join(CSRC, "libplo_cuda.so")
 
 PLO_OK = 0
 ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "NO_DEVICE", -4: "UNSUPPORTED", -5: "STATE"}
@@ -70,7 +71,7 @@ EXPORTS = [
     "plo_create", "plo_destroy", "plo_last_error", "plo_version", "plo_set_stream", "plo_synchronize",
     "plo_default_params", "plo_set_params", "plo_set_target", "plo_set_source", "plo_set_target_device",
     "plo_set_source_device", "plo_target_size", "plo_source_size", "plo_project", "plo_get_pairs",
-    "plo_get_neighbors", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls", "plo_solve_ls", "plo_solve_ransac",
+    "plo_get_neighbors", "plo_last_project_times", "plo_get_search_stats", "plo_get_query_results", "plo_get_target_normals", "plo_solve_wls", "plo_solve_ls", "plo_solve_ransac",
     "plo_solve_wls_host", "plo_get_normal_equations", "plo_register", "plo_register_batch",
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
     "plo_last_kernel_timings", "plo_map_reset", "plo_map_push", "plo_map_push_device", "plo_map_info", "plo_map_get",
@@ -131,6 +132,7 @@ def lib() -> C.CDLL:
     L.plo_time_project_kernel.argtypes = [vp, vp, i32, C.POINTER(C.c_float)]
     L.plo_set_profiling.argtypes = [vp, i32]
     L.plo_last_kernel_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.plo_last_project_times.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.plo_map_reset.argtypes = [vp]
     L.plo_map_push.argtypes = [vp, vp, i64, i32, vp, i32, i32, i32]
     L.plo_map_push_device.argtypes = [vp, vp, i64, i32, vp, i32, i32, i32]

@@ -317,6 +317,13 @@ class Context:
         self._ck(self.L.plo_last_kernel_timings(self.h, C.byref(ms), C.byref(n)))
         return dict(ms_project_mean=ms.value, n_project=n.value)
 
+    def last_project_times(self) -> np.ndarray:
+        """device ms of every projection launch of the last register() (profiling mode), one per ICP iteration"""
+        ms = np.zeros(64, np.float32)
+        n = C.c_int32()
+        self._ck(self.L.plo_last_project_times(self.h, _ptr(ms), 64, C.byref(n)))
+        return ms[: n.value].copy()
+
     def time_project_kernel(self, T=None, reps: int = 10) -> float:
         T = np.ascontiguousarray(np.eye(4) if T is None else T, dtype=np.float64).reshape(16)
         ms = C.c_float()

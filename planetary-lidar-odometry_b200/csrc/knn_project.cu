@@ -10,7 +10,9 @@
 //   A  bound: an upper bound D of the k-th neighbour distance (squared).  Triangle inequality
 //      on a reference whose k-th distance is known — the same query in the previous ICP
 //      iteration (temporal) or the previous query of the warp's chunk (carry; LiDAR clouds
-//      arrive in scan order) — D = (sqrt(kd2_ref) + |x - x_ref|)^2, inflated by 1e-9.  Without
+//      arrive in scan order) — D = (sqrt(kd2_ref) + |x - x_ref|)^2, inflated by 1e-9; for the
+//      carry reference also the farthest of ITS k neighbours as seen from x (k distinct points
+//      within that distance: adjacent scan points share most neighbours).  Without
 //      a useful reference: greedy descent to the nearest leaves and the k-th smallest
 //      rounded-up distance among their points (bitonic sort / merge across the warp).
 //   B  collect (fp32, conservative): depth-first walk; boxes and points are tested with
@@ -25,6 +27,20 @@
 //      ranks < k are scattered to their slot: lane j then holds the j-th neighbour.
 // Exactness: a point is only ever skipped when a LOWER bound of its distance exceeds an
 // UPPER bound of the k-th distance; the final order is decided on the exact fp64 values.
+//
+// Candidate cache (k_project only; opt-in at compile time, -DPLO_CACHE: it makes the late projections
+// 12 % faster and the first three slower, a net loss on a 7-iteration registration -- see DESIGN.md 3.2).
+// ICP re-projects the SAME source against the SAME map ~7 times and
+// after the second iteration a query moves by millimetres, so phase B mostly re-discovers the
+// leaves it found last time.  A walk therefore leaves behind, per query, up to kCacheN candidate
+// positions, the query position x_ref it was made from and a radius e2 such that EVERY map point
+// outside the cache has d2(x_ref, p) > e2.  A later projection with a proven k-th-distance bound D
+// (phase A, temporal) and displacement delta = |x - x_ref| may skip the walk when
+// sqrt(D) + delta <= sqrt(e2) (all in float, rounded against the claim): a point outside the cache
+// is then farther than sqrt(e2) - delta >= sqrt(D) from x, i.e. not a candidate, so scanning the
+// cached positions with the same lower-bound test yields the same superset the walk would, and
+// phase C decides on exact fp64 values as always.  When the test fails the walk runs (with the
+// bound inflated so that the cache gets a margin) and refreshes the cache.
 //
 // The 1-NN of :601-609 (no self match) is the first list entry with d2 > DBL_EPSILON;
 // only if the list is full of coincident points is a second (k=1) search needed.
@@ -44,6 +60,16 @@ namespace {
 
 constexpr int kCap = 128;          // candidate buffer entries per warp
 constexpr int kWarpsPerBlock = 8;
+// Candidate cache: measured, NOT in the default build -- compile with -DPLO_CACHE to enable
+#ifdef PLO_CACHE
+constexpr bool kUseCache = true;
+#else
+constexpr bool kUseCache = false;
+#endif
+constexpr int kCacheN = 64;        // cached candidate positions per query (two per lane)
+#ifndef PLO_CACHE_INFLATE
+#define PLO_CACHE_INFLATE 3.2f     // refresh walk: bound (squared) = this x the k-th distance of the bound's reference
+#endif
 #ifndef PLO_GREEDY_LEAVES
 #define PLO_GREEDY_LEAVES 2
 #endif
@@ -194,6 +220,27 @@ __device__ __forceinline__ void rank_select(WarpScratch& ws, int C, int k, int l
   ws.oidx[lane] = -1;
   ws.opos[lane] = -1;
   __syncwarp();
+#ifndef PLO_NO_FASTRANK
+  if (C <= 32) {
+    // the common case, one candidate per lane: rank by distance alone (one broadcast load and one
+    // compare per candidate); the index order is only consulted when two distances are bit-equal
+    const bool own = lane < C;
+    const double d = own ? ws.d2[lane] : CUDART_INF;
+    const int x = own ? ws.idx[lane] : 0x7fffffff;
+    int r = 0;
+#pragma unroll 4
+    for (int j = 0; j < C; ++j) r += (ws.d2[j] < d) ? 1 : 0;
+    const unsigned same = __match_any_sync(PLO_FULL_MASK, __double_as_longlong(d));   // executed by all 32 lanes
+    const bool tied = own && d < CUDART_INF && __popc(same) > 1;
+    if (__any_sync(PLO_FULL_MASK, tied)) {
+      if (tied)
+        for (int j = 0; j < C; ++j) r += (ws.d2[j] == d && ws.idx[j] < x) ? 1 : 0;
+    }
+    if (own && r < k && d < CUDART_INF) { ws.od2[r] = d; ws.oidx[r] = x; ws.opos[r] = ws.pos[lane]; }
+    __syncwarp();
+    return;
+  }
+#endif
   for (int base = 0; base < C; base += 64) {
     const int i0 = base + lane, i1 = base + 32 + lane;
     const bool own0 = i0 < C, own1 = i1 < C;
@@ -367,13 +414,104 @@ struct Collect {
   }
 };
 
+// per-query candidate cache in global memory (see the file header)
+struct QueryCache {
+  int* pos;      // [kCacheN] positions in the sorted arrays, -1 = empty
+  float4* cx;    // x_ref.xyz, w = e2 (<= 0: no valid cache)
+  bool read;     // a previous projection of the same clouds wrote it
+  bool widen;    // the pose is settling: a refresh walk may look farther than it must (margin for the next moves)
+};
+
+// upper bound of |a - b|
+__device__ __forceinline__ float dist_hi(float x, float y, float z, float rx, float ry, float rz) {
+  const float ax = fmaxf(fabsf(__fsub_ru(x, rx)), fabsf(__fsub_rd(x, rx)));
+  const float ay = fmaxf(fabsf(__fsub_ru(y, ry)), fabsf(__fsub_rd(y, ry)));
+  const float az = fmaxf(fabsf(__fsub_ru(z, rz)), fabsf(__fsub_rd(z, rz)));
+  return __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(ax, ax), __fmul_ru(ay, ay)), __fmul_ru(az, az)));
+}
+
+// phase B from the cache: the cached positions against the bound, same lower-bound test as a leaf scan
+__device__ __forceinline__ void collect_cached(const MapView& m, const int* __restrict__ cpos, float qx, float qy, float qz,
+                                               WarpScratch& ws, Collector& col, int lane) {
+#pragma unroll
+  for (int h = 0; h < kCacheN / 32; ++h) {
+    const int ps = cpos[h * 32 + lane];
+    bool pass = false;
+    float lo = 0.f;
+    if (ps >= 0) {
+      lo = dist_lo2(qx, qy, qz, __ldg(&m.pts[ps]));
+      pass = lo <= col.Df;
+    }
+    const unsigned b = __ballot_sync(PLO_FULL_MASK, pass);
+    if (pass) {
+      const int o = col.count + __popc(b & ((1u << lane) - 1u));
+      ws.lo[o] = lo;
+      ws.pos[o] = ps;
+    }
+    col.count += __popc(b);
+  }
+  col.appended += col.count;
+}
+
+// after a walk: the buffer holds every point with lo <= Df.  Keep at most kCacheN of them (threshold t <= Df
+// lowered until they fit): every point outside then has d2 >= lo > t.
+__device__ __forceinline__ void store_cache(const QueryCache& qc, WarpScratch& ws, const Collector& col, float qx, float qy,
+                                            float qz, int lane) {
+  __syncwarp();
+  float t = col.Df;
+  int cnt = col.count;
+  for (int pass = 0; cnt > kCacheN && pass < 24; ++pass) {   // 0.8^24 < 0.005: beyond that (ties at zero distance) no cache
+    t = __fmul_rd(t, 0.8f);
+    cnt = 0;
+    for (int base = 0; base < col.count; base += 32) {
+      const int i = base + lane;
+      cnt += __popc(__ballot_sync(PLO_FULL_MASK, i < col.count && ws.lo[i] <= t));
+    }
+  }
+  int o = 0;
+  for (int base = 0; base < col.count; base += 32) {
+    const int i = base + lane;
+    const bool keep = cnt <= kCacheN && i < col.count && ws.lo[i] <= t;
+    const unsigned b = __ballot_sync(PLO_FULL_MASK, keep);
+    if (keep) qc.pos[o + __popc(b & ((1u << lane) - 1u))] = ws.pos[i];
+    o += __popc(b);
+  }
+  for (int i = o + lane; i < kCacheN; i += 32) qc.pos[i] = -1;
+  // a bound that met the massive-tie fallback (exact_shrink) no longer describes the buffer: no cache
+  const bool valid = cnt <= kCacheN && col.shrinks < 1000 && t > 0.f && t < CUDART_INF_F;
+  if (lane == 0) *qc.cx = make_float4(qx, qy, qz, valid ? t : -1.f);
+}
+
+// keep the buffered candidates with lo <= t (stable, in place)
+__device__ __forceinline__ int filter_buffer(WarpScratch& ws, int count, float t, int lane) {
+  int kept = 0;
+  for (int base = 0; base < count; base += 32) {
+    const int i = base + lane;
+    float l = 0.f;
+    int ps = 0;
+    bool keepit = false;
+    if (i < count) { l = ws.lo[i]; ps = ws.pos[i]; keepit = l <= t; }
+    const unsigned b = __ballot_sync(PLO_FULL_MASK, keepit);
+    __syncwarp();
+    if (keepit) {
+      const int o = kept + __popc(b & ((1u << lane) - 1u));
+      ws.lo[o] = l;
+      ws.pos[o] = ps;
+    }
+    kept += __popc(b);
+    __syncwarp();
+  }
+  return kept;
+}
+
 // exact k-NN of q (float32 coordinates, as the reference stores the transformed point).
 // Df0: float threshold derived from a proven upper bound of the k-th distance (squared), or +inf;
 // with `refine` the greedy bound is evaluated as well and the walk is ordered.
 // Result: lane j holds neighbour j (d2 = +inf where not filled).
-template <int LEVELS>
+template <int LEVELS, bool CACHE = false>
 __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, float qz, float Df0, bool refine, double r2,
-                                         int k, bool allow_self, WarpScratch& ws, TopK& tk, SearchStats& st, int lane) {
+                                         int k, bool allow_self, WarpScratch& ws, TopK& tk, SearchStats& st, int lane,
+                                         const QueryCache* qc = nullptr, float ref_kf = 0.f) {
   st.n_leaf = st.n_node = st.n_cand = 0;
   tk.d2 = CUDART_INF;
   tk.idx = -1;
@@ -385,16 +523,42 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
   col.count = 0;
   col.appended = 0;
   col.shrinks = 0;
-  if (refine) {
-    const unsigned best = Greedy<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, allow_self, st, lane);
-    const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
-    if (kth < 0x7f800000u) col.Df = fminf(col.Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
-    Collect<LEVELS, true>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
-  } else {
-    Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+  bool walked = true;
+  if constexpr (CACHE) {
+    if (qc->read && !refine) {
+      const float4 cx = *qc->cx;
+      // sqrt(D) + |x - x_ref| <= sqrt(e2), rounded against the claim (NaN compares false)
+      if (cx.w > 0.f && __fadd_ru(__fsqrt_ru(col.Df), dist_hi(qx, qy, qz, cx.x, cx.y, cx.z)) <= __fsqrt_rd(cx.w)) {
+        collect_cached(m, qc->pos, qx, qy, qz, ws, col, lane);
+        walked = false;
+      }
+    }
+  }
+  if (walked) {
+    if (refine) {
+      const unsigned best = Greedy<LEVELS>::run(m, 0, qx, qy, qz, r2f_lo, allow_self, st, lane);
+      const unsigned kth = __shfl_sync(PLO_FULL_MASK, best, k - 1);
+      if (kth < 0x7f800000u) col.Df = fminf(col.Df, __fmul_ru(__uint_as_float(kth), 1.000001f));
+      Collect<LEVELS, true>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+      if constexpr (CACHE) store_cache(*qc, ws, col, qx, qy, qz, lane);
+    } else if constexpr (CACHE) {
+      // refresh walk: a wider ball, so that the cache outlives the next small moves of the query
+      // (PLO_CACHE_INFLATE x the reference's k-th distance, unless the proven bound is already looser)
+      const float tight = col.Df;
+      if (qc->widen) col.Df = fminf(fmaxf(tight, __fmul_ru(ref_kf, PLO_CACHE_INFLATE)), bound_f(r2));
+      Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+      store_cache(*qc, ws, col, qx, qy, qz, lane);
+      if (tight < col.Df) {   // back to the proven bound for phase C
+        __syncwarp();
+        col.count = filter_buffer(ws, col.count, tight, lane);
+        col.Df = tight;
+      }
+    } else {
+      Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
+    }
   }
   __syncwarp();
-  if (st.on) st.n_cand = col.appended + 100000 * col.shrinks;
+  if (st.on) st.n_cand = col.appended + 100000 * col.shrinks + (walked ? 0 : 50000);
   if (col.count > 32) {
     // more than a warp's worth of candidates: a float k-th bound drops most of the surplus before
     // the O(C^2 / 32) exact ranking
@@ -454,6 +618,8 @@ struct ProjectOut {
   float4* qn;        // normal of the 1-NN (float32)
   int* status;
   float* kd2f;       // k-th neighbour distance (squared, rounded up) of this projection; +inf if the list is not full
+  int* cache_pos;    // [M * kCacheN] candidate cache (file header)
+  float4* cache_cx;  // [M] x_ref + e2 of the cache
   // hooks
   double* height;
   int* nn1_idx;
@@ -476,6 +642,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   const int lane = threadIdx.x & 31;
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const int use_prev = st->use_prev;
+  const int warm = st->warm;
   const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
@@ -493,6 +660,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
    c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
    if (c0 >= n_src) break;
    float carry_kf = CUDART_INF_F, carry_x = 0.f, carry_y = 0.f, carry_z = 0.f;
+   int carry_pos = -1;   // lane j < k: position of the previous query's j-th neighbour (valid while carry_kf is finite)
    const int c1 = min(c0 + chunk, n_src);
    for (int qi = c0; qi < c1; ++qi) {
     const float4 p = __ldg(&sp[qi]);
@@ -528,6 +696,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
     if (carry_kf < CUDART_INF_F) {
       const float Dc = tri_bound(carry_kf, xf, yf, zf, carry_x, carry_y, carry_z);
       if (Dc < Df0) { Df0 = Dc; ref_kf = carry_kf; }
+#ifndef PLO_NO_CARRY_LIST
+      // the previous query's k neighbours are k distinct map points: the farthest of them from x bounds the
+      // k-th distance of x as well (adjacent scan points share most neighbours: far tighter than the triangle)
+      float hi = 0.f;
+      if (lane < P.k) hi = hi_from_lo(dist_lo2(xf, yf, zf, __ldg(&m.pts[carry_pos])));
+      const float Dn = __uint_as_float(__reduce_max_sync(PLO_FULL_MASK, __float_as_uint(hi)));
+      if (Dn < Df0 && Dn <= __double2float_rd(P.r2)) { Df0 = __fmul_ru(Dn, 1.000001f); ref_kf = Df0; }
+#endif
     }
     if (!(Df0 == Df0)) Df0 = CUDART_INF_F;
     // a bound more than 2.5x (in distance) above its reference would buffer > 6x k candidates:
@@ -537,12 +713,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
     TopK tk;
     SearchStats ss;
     ss.on = HOOKS;
-    if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane);   // :372-375 ALLOW_SELF_MATCH
+    QueryCache qc;
+    qc.pos = out.cache_pos + (size_t)qi * kCacheN;
+    qc.cx = out.cache_cx + qi;
+    qc.read = use_prev != 0;
+    qc.widen = warm != 0;
+    if (n_tgt > 0) knn_topk<LEVELS, kUseCache>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane, &qc, ref_kf);   // :372-375 ALLOW_SELF_MATCH
     else { tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1; ss.n_leaf = ss.n_node = ss.n_cand = 0; }
     const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
     const double kd2_now = __shfl_sync(PLO_FULL_MASK, tk.d2, P.k - 1);
     const float kd2f_now = (kd2_now < CUDART_INF) ? __double2float_ru(kd2_now) : CUDART_INF_F;
     carry_kf = kd2f_now; carry_x = xf; carry_y = yf; carry_z = zf;
+    carry_pos = tk.pos;
 
     // ---- 1-NN without self match (:601-609) ----
     int i1 = -1, pos1 = -1;
@@ -719,6 +901,10 @@ int plo_reserve_query_buffers(plo_ctx* c, bool hooks) {
   PLO_CUDA(c, c->q_n.reserve(sizeof(float4) * m));
   PLO_CUDA(c, c->q_status.reserve(sizeof(int) * m));
   PLO_CUDA(c, c->q_kd2.reserve(sizeof(double) * m));
+  if (kUseCache) {
+    PLO_CUDA(c, c->q_cache_pos.reserve(sizeof(int) * kCacheN * m));
+    PLO_CUDA(c, c->q_cache_cx.reserve(sizeof(float4) * m));
+  }
   if (hooks) {
     PLO_CUDA(c, c->q_height.reserve(sizeof(double) * m));
     PLO_CUDA(c, c->q_nn1_idx.reserve(sizeof(int) * m));
@@ -812,6 +998,7 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   out.qx = c->q_x.as<float4>(); out.qy = c->q_y.as<float4>(); out.qn = c->q_n.as<float4>();
   out.status = c->q_status.as<int>();
   out.kd2f = c->q_kd2.as<float>();
+  out.cache_pos = c->q_cache_pos.as<int>(); out.cache_cx = c->q_cache_cx.as<float4>();
   out.height = c->q_height.as<double>(); out.nn1_idx = c->q_nn1_idx.as<int>(); out.nn1_d2 = c->q_nn1_d2.as<double>();
   out.nn_idx = c->q_nn_idx.as<int>(); out.nn_d2 = c->q_nn_d2.as<double>();
   out.search_stats = c->q_stats.as<int>();

@@ -436,6 +436,7 @@ __device__ void finish_iteration(DevState* __restrict__ st, const DevParams& P, 
   // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
   // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
   st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
+  st->warm = (dd < 0.05 && da < 0.01) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
   if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
   else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
   if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
@@ -873,6 +874,7 @@ __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
     st->done = 0;
     st->use_prev = use_prev;
     st->chunk = use_prev ? PLO_CHUNK_MID : PLO_CHUNK_COLD;
+    st->warm = 0;
   }
 }
 

@@ -179,7 +179,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_cache_pos, &c->q_cache_cx,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
@@ -659,7 +659,7 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   add(c->pts_sorted.p); add(c->nrm_sorted.p); add(c->nrm_pca.p);
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
   add(c->s_order.p); v.push_back(c->tile_mode ? 1ull : 0ull);
-  add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p);
+  add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p); add(c->q_cache_pos.p); add(c->q_cache_cx.p);
   add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
   add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);
   add(c->ransac_mind.p); add(c->partials2.p); add(c->h_src.p); add(c->h_ref.p); add(c->h_nrm.p); add(c->h_w.p); add(c->blockcnt.p);
@@ -803,6 +803,7 @@ int plo_register(plo_ctx* c, const double T0[16], double T[16], plo_reg_stats* s
       float ms = 0.f;
       cudaEventElapsedTime(&ms, c->ev_proj[2 * it], c->ev_proj[2 * it + 1]);
       total += ms;
+      if (it < 64) c->ms_project_each[it] = ms;
     }
     c->n_project = n;
     c->ms_project_mean = n > 0 ? total / n : 0.f;
@@ -820,6 +821,15 @@ int plo_last_kernel_timings(plo_ctx* c, float* ms_project_mean, int32_t* n_proje
   if (!c) return PLO_ERR_INVALID_ARG;
   if (ms_project_mean) *ms_project_mean = c->ms_project_mean;
   if (n_project) *n_project = c->n_project;
+  return PLO_OK;
+}
+
+int plo_last_project_times(plo_ctx* c, float* ms_each, int32_t cap, int32_t* n_project) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  const int n = std::min(c->n_project, 64);
+  if (ms_each)
+    for (int i = 0; i < n && i < cap; ++i) ms_each[i] = c->ms_project_each[i];
+  if (n_project) *n_project = n;
   return PLO_OK;
 }
 

@@ -70,6 +70,8 @@ struct DevState {
   int done;       // kernels of later iterations return immediately when set
   int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds (temporal bound usable)
   int chunk;      // consecutive source points per warp in the next projection (carry bound vs. balance)
+  int warm;       // the last pose step was small: the next projection's queries barely move (candidate cache pays)
+  int pad1;
 };
 
 struct DevCounts {
@@ -151,6 +153,7 @@ struct plo_ctx {
 
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
+  DevBuf q_cache_pos, q_cache_cx;   // per-query candidate cache of k_project (knn_project.cu header)
   bool prev_valid = false;   // q_x / q_kd2 hold the previous projection of the SAME clouds and k, r
   bool hooks_valid = false;
   DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2, q_stats;
@@ -180,6 +183,7 @@ struct plo_ctx {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_proj;   // 2 per loop iteration when profiling
   float ms_project_mean = 0.f;
+  float ms_project_each[64] = {0.f};   // per ICP iteration (profiling mode)
   int n_project = 0;
 
   MapView map_view() const;

@@ -1,0 +1,33 @@
+"""A/B timing of one build (PLO_LIB selects it) on the north-star workload: registration time (CUDA graph,
+events), per-launch k_project time over the 7 iterations (profiling mode) and a pose / pair-count
+fingerprint that must not change between builds.  usage: PLO_LIB=... python tools/probe_ab.py [tag]"""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import plo_b200 as plo
+tag = sys.argv[1] if len(sys.argv) > 1 else "default"
+cache = "/tmp/plo_pair.npz"
+if os.path.exists(cache):
+    z = np.load(cache); target, source = z["t"], z["s"]
+else:
+    pair = plo.synth.workloads.hdl64_vs_map(); target, source = pair.target, pair.source
+    np.savez(cache, t=target, s=source)
+import torch
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ctx = plo.Context(0)
+regs = []
+for i in range(8):
+    ctx.set_target(target); ctx.set_source(source)
+    flush.zero_(); torch.cuda.synchronize()
+    T, rs = ctx.register()
+    if i >= 2: regs.append(ctx.last_timings()["ms_register"])
+ctx.set_profiling(True)
+kp = []
+for i in range(3):
+    ctx.set_target(target); ctx.set_source(source); T, rs = ctx.register(); kp.append(ctx.last_kernel_timings()["ms_project_mean"]); each = ctx.last_project_times()
+ctx.set_profiling(False)
+steady = ctx.time_project_kernel(T, 10)
+fp = float(np.abs(T).sum())
+print(f"[{tag}] iters {rs['iters']} pairs {rs['pairs']} fp {fp:.12f} | register ms median {np.median(regs):.4f} min {np.min(regs):.4f} | "
+      f"k_project mean/launch {np.mean(kp):.4f} | steady (converged pose) {steady:.4f} | per launch {np.round(each, 3).tolist()}", flush=True)
