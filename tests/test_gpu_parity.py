@@ -576,6 +576,64 @@ def test_randomised_small_clouds_fuzz(oracle_mod):
         ctx.close()
 
 
+def test_carry_bounds_along_the_scan_order(oracle_mod, monkeypatch):
+    """Chunks of consecutive source points per warp (PLO_CHUNK forces them on small clouds): the bound of a
+    query then comes from the previous query of its chunk -- triangle inequality on its k-th distance and the
+    farthest of its k neighbours.  Sorted, shuffled, duplicated and far-apart consecutive queries, quantised
+    maps (ties at the bound), lists that are not full: neighbour sets, statuses and counters stay exact."""
+    rng = np.random.default_rng(77)
+    for chunk in (2, 8, 64):
+        monkeypatch.setenv("PLO_CHUNK", str(chunk))
+        for trial in range(8):
+            n_t = int(rng.choice([40, 700, 5000, 33000]))
+            n_s = int(rng.choice([64, 500, 3000]))
+            xyz = rng.uniform(-4, 4, size=(n_t, 3)) * [1, 1, 0.02]
+            if trial % 2:
+                xyz = np.round(xyz * 8) / 8
+            tgt = np.zeros((n_t, 12), np.float32)
+            tgt[:, 0:3] = xyz
+            tgt[:, 4:7] = [0, 0, 1]
+            src = np.zeros((n_s, 12), np.float32)
+            line = np.linspace(-4, 4, n_s)
+            src[:, 0] = line                                  # a scan line: neighbours in memory are neighbours in space
+            src[:, 1] = 0.3 * np.sin(line)
+            if trial % 4 == 1:
+                src[:, 0:3] = xyz[rng.integers(0, n_t, n_s)]      # unrelated consecutive queries, exact hits on map points
+            if trial % 4 == 2:
+                m3 = src[1::3].shape[0]
+                src[0:3 * m3:3, 0:3] = src[1::3, 0:3]             # duplicated consecutive queries
+            if trial % 4 == 3:
+                src[::7, 0] += 50.0                               # every 7th query far from everything (empty list in between)
+            src[:, 4:7] = [0, 0, 1]
+            kw = dict(search_number=int(rng.choice([3, 20, 32])), r=float(rng.choice([0.5, 3.0])), h=1.0)
+            ctx, orc = _both(oracle_mod, tgt, src, **kw)
+            try:
+                _check_projection(ctx, orc)
+                _check_projection(ctx, orc, T=plo.synth.scenes.pose_matrix([0.3, -0.1, 0.0], yaw_deg=1.0))
+            except AssertionError as e:
+                raise AssertionError(f"chunk {chunk} trial {trial}: n_t={n_t} n_s={n_s} {kw}: {e}") from e
+            ctx.close()
+
+
+def test_per_launch_projection_times(oracle_mod):
+    """plo_last_project_times: one device time per ICP iteration of the last registration (profiling mode)."""
+    pair = W.hdl64_pair(max_source=20000)
+    ctx = plo.Context(0)
+    ctx.set_target(pair.target)
+    ctx.set_source(pair.source)
+    T0, s0 = ctx.register()
+    ctx.set_profiling(True)
+    ctx.set_target(pair.target)
+    ctx.set_source(pair.source)
+    T1, s1 = ctx.register()
+    each = ctx.last_project_times()
+    mean = ctx.last_kernel_timings()
+    ctx.set_profiling(False)
+    assert np.array_equal(T0, T1) and s0["iters"] == s1["iters"]          # enqueue-all path == graph path, bitwise
+    assert each.shape[0] == mean["n_project"] == s1["iters"] and (each > 0).all()
+    assert abs(each.mean() - mean["ms_project_mean"]) < 1e-4
+
+
 def test_trimmed_ls_solver(oracle_mod):
     """"next" row of SURVEY.md §8f, rank 2: SolveMotionEstimationProblemLS (src/solver.cpp:74-166) on the
     device — first LS, |residual| rank window [thr*N, (1-thr)*N] by a stable radix sort, second LS."""
