@@ -118,9 +118,10 @@ class IMLSICPMatcherCUDA {
       params_.ls_threshold = ls_threshold;
     } else if (solve_method == "RANSAC") {
       params_.solver = PLO_SOLVER_RANSAC;
-      if (final_solve_method == "Weighted LS") params_.ransac_final = PLO_FINAL_WLS;
+      if (final_solve_method == "LS") { params_.ransac_final = PLO_FINAL_LS; params_.ls_threshold = ls_threshold; }
+      else if (final_solve_method == "Weighted LS") params_.ransac_final = PLO_FINAL_WLS;
       else if (final_solve_method == "DRPM") params_.ransac_final = PLO_FINAL_DRPM;
-      else throw std::runtime_error("plo: RANSAC final_solve_method \"" + final_solve_method + "\" does not run on the device");
+      else throw std::runtime_error("plo: unknown RANSAC final_solve_method \"" + final_solve_method + "\"");
       params_.ransac_distance_threshold = ransac_distance_threshold;
       params_.huber_threshold = huber_threshold;
       params_.ransac_max_iterations = ransac_max_iterations;

@@ -73,11 +73,12 @@ typedef enum plo_solver {
                       /* the pairs whose |residual| rank lies in [thr*N, (1-thr)*N] (2 % / 98 % trim)    */
   PLO_SOLVER_RANSAC = 2 /* SolveMotionEstimationProblemRANSAC, src/solver.cpp:222-385 — the config.json   */
                       /* default chain: FPS-3 hypotheses, inlier count, Huber/exp weights at the best     */
-                      /* hypothesis, then ransac_final (Weighted LS or DRPM, :499-603).  The reference's   */
+                      /* hypothesis, then ransac_final (LS, Weighted LS or DRPM :499-603).  The reference's  */
                       /* unseeded rand() (src/common.cpp:49) is replaced by xorshift64(ransac_seed).        */
 } plo_solver;
 
 typedef enum plo_ransac_final {
+  PLO_FINAL_LS = 0,   /* "LS": trimmed LS (src/solver.cpp:74-166) on the inliers of the best hypothesis, :366-371 */
   PLO_FINAL_WLS = 1,  /* "Weighted LS" */
   PLO_FINAL_DRPM = 2  /* "DRPM" (config.json default) */
 } plo_ransac_final;

@@ -20,7 +20,7 @@ POINT_STATUS = ["ok", "no_normal", "too_far", "invalid_normal", "normal_constrai
 REG_STATUS = {1: "CONVERGED", 2: "MAX_ITERS", 3: "TOO_FEW_PAIRS", 4: "SOLVE_FAILED"}
 W_UNIT, W_HUBER_EXP = 0, 1
 SOLVER_WLS, SOLVER_LS, SOLVER_RANSAC = 0, 1, 2
-FINAL_WLS, FINAL_DRPM = 1, 2
+FINAL_LS, FINAL_WLS, FINAL_DRPM = 0, 1, 2
 
 
 class PloError(RuntimeError):

@@ -108,13 +108,14 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
     elif smethod == "RANSAC":
         solver = _lib.SOLVER_RANSAC
         final = _get(sm, "RANSAC", "final_solve_method")
-        if final == "Weighted LS":
+        if final == "LS":
+            ransac_final = _lib.FINAL_LS
+        elif final == "Weighted LS":
             ransac_final = _lib.FINAL_WLS
         elif final == "DRPM":
             ransac_final = _lib.FINAL_DRPM
-        else:
-            raise ConfigError(f'solve_method RANSAC -> "{final}": only final_solve_method "Weighted LS" and "DRPM" '
-                              'run on the device')
+        else:   # the reference prints "Invalid FINAL_SOLVE_METHOD in RANSAC!" and returns false (src/solver.cpp:380-384)
+            raise ConfigError(f'solve_method RANSAC -> unknown final_solve_method "{final}"')
     elif smethod in ("Ceres", "ICP", "Teaser"):
         raise ConfigError(f'solve_method "{smethod}" is outside the hot-path scope (SURVEY.md §2.1 row 2)')
     else:

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
                                                                  const DevCounts* __restrict__ counts,
                                                                  const DevState* __restrict__ st, DevParams P,
                                                                  double* __restrict__ partials, int respect_done,
-                                                                 const int* __restrict__ mask) {
+                                                                 const int* __restrict__ mask, int inliers_unit) {
   if (respect_done && st->done) return;
   double acc[PLO_NSUM];
 #pragma unroll
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
     if (P.weight_mode == PLO_W_HUBER_EXP) {
       w = huber_exp_weight(Tw, s, d, n, P);
       if (w < 0.0) continue;
+      if (inliers_unit) w = 1.0;   // RANSAC -> "LS": the inlier subset, unweighted (src/solver.cpp:366-371)
     }
     accumulate_pair(acc, s, d, n, w);
   }
@@ -811,12 +812,16 @@ __global__ void __launch_bounds__(64) k_drpm_finish(const double* __restrict__ p
 __global__ void __launch_bounds__(256) k_ls_keys(const float4* __restrict__ qx, const float4* __restrict__ qy,
                                                  const float4* __restrict__ qn, const DevCounts* __restrict__ counts,
                                                  const DevState* __restrict__ st, int respect_done, int m_raw,
-                                                 unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+                                                 unsigned long long* __restrict__ keys, int* __restrict__ vals, DevParams P,
+                                                 int inliers_only) {
   if (respect_done && st->done) return;
   const int n_src = counts->n_source;
   double x0[6];
 #pragma unroll
   for (int a = 0; a < 6; ++a) x0[a] = st->x0[a];
+  double Tw[16];   // RANSAC -> "LS": only the inliers of the best hypothesis enter the trimmed solve
+#pragma unroll
+  for (int t = 0; t < 16; ++t) Tw[t] = inliers_only ? st->Tbest[t] : ((t % 5 == 0) ? 1.0 : 0.0);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m_raw; i += gridDim.x * blockDim.x) {
     unsigned long long key = 0xffffffffffffffffull;
     if (i < n_src) {
@@ -832,7 +837,8 @@ __global__ void __launch_bounds__(256) k_ls_keys(const float4* __restrict__ qx, 
         double r = 0.0;
 #pragma unroll
         for (int t = 0; t < 6; ++t) r += a[t] * x0[t];
-        key = (unsigned long long)__double_as_longlong(fabs(r - b));   // non-negative doubles order like their bits
+        if (!inliers_only || huber_exp_weight(Tw, s, d, n, P) >= 0.0)
+          key = (unsigned long long)__double_as_longlong(fabs(r - b));   // non-negative doubles order like their bits
       }
     }
     keys[i] = key;
@@ -842,9 +848,11 @@ __global__ void __launch_bounds__(256) k_ls_keys(const float4* __restrict__ qx, 
 
 // rank window [thr*N, (1-thr)*N] of the sorted pairs -> per-source-point mask (src/solver.cpp:124-134)
 __global__ void __launch_bounds__(256) k_ls_select(const int* __restrict__ vals_sorted, const DevState* __restrict__ st,
-                                                   int respect_done, int m_raw, double threshold, int* __restrict__ mask) {
+                                                   int respect_done, int m_raw, double threshold, int* __restrict__ mask,
+                                                   int n_from_weights) {
   if (respect_done && st->done) return;
-  const long long N = st->pairs;
+  // rows of the first pass: all surviving pairs, or (RANSAC -> "LS") the inliers, whose unit weights sum to their count
+  const long long N = n_from_weights ? (long long)st->sw : st->pairs;
   const long long lower = (long long)(threshold * (double)N);
   long long upper = (long long)((1.0 - threshold) * (double)N);
   if (upper > N - 1) upper = N - 1;   // the reference reads one past the end at threshold = 0
@@ -956,7 +964,8 @@ constexpr int kLsPasses = 7;   // 64-bit keys, 10-bit digits
 
 int plo_reserve_solver_buffers(plo_ctx* c) {
   PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
-  if (c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0) {
+  const bool trims = c->dprm.solver == PLO_SOLVER_LS || (c->dprm.solver == PLO_SOLVER_RANSAC && c->dprm.ransac_final == PLO_FINAL_LS);
+  if (trims && c->m_raw > 0) {
     const size_t m = (size_t)c->m_raw;
     for (int a = 0; a < 2; ++a) {
       PLO_CUDA(c, c->ls_keys[a].reserve(sizeof(unsigned long long) * m));
@@ -985,11 +994,14 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   const int adv = advance_loop ? 1 : 0;
   const cudaGraphConditionalHandle cond = (cudaGraphConditionalHandle)cond_handle;
   const int use_cond = cond_handle ? 1 : 0;
-  const bool trimmed = c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0;
   const bool ransac = c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0;
+  const bool ransac_ls = ransac && c->dprm.ransac_final == PLO_FINAL_LS;   // trimmed LS on the inliers (src/solver.cpp:366-371)
+  const bool trimmed = (c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0) || ransac_ls;
+  const int in_unit = ransac_ls ? 1 : 0;
   DevParams P = c->dprm;
   if (trimmed) P.weight_mode = PLO_W_UNIT;       // SolveMotionEstimationProblemLS is unweighted
-  if (ransac) P.weight_mode = PLO_W_HUBER_EXP;   // Huber/exp weights at the best hypothesis (src/solver.cpp:334-364)
+  if (ransac) P.weight_mode = PLO_W_HUBER_EXP;   // Huber/exp weights at the best hypothesis (src/solver.cpp:334-364);
+                                                 // with final "LS" only their inlier test is used (in_unit)
   if (c->dprm.solver == PLO_SOLVER_RANSAC && !ransac) P.solver = PLO_SOLVER_WLS;   // empty source: nothing to sample
   if (ransac) {
     // the hypothesis sampler works on the compacted pair list (indices = positions in source_cloud)
@@ -1002,7 +1014,7 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   if (c->m_raw > 0) {
     k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                         c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
-                                                        c->partials.as<double>(), adv, nullptr);
+                                                        c->partials.as<double>(), adv, nullptr, in_unit);
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
   }
@@ -1031,19 +1043,21 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   const int gk = (int)std::max<int64_t>(1, std::min<int64_t>((m + 255) / 256, (int64_t)plo_grid(c, 4)));
   k_ls_keys<<<gk, 256, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(), c->counts.as<DevCounts>(),
                                        c->state.as<DevState>(), adv, m, c->ls_keys[0].as<unsigned long long>(),
-                                       c->ls_vals[0].as<int>());
+                                       c->ls_vals[0].as<int>(), P, in_unit);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   unsigned long long* keys[2] = {c->ls_keys[0].as<unsigned long long>(), c->ls_keys[1].as<unsigned long long>()};
   int* vals[2] = {c->ls_vals[0].as<int>(), c->ls_vals[1].as<int>()};
   int which = 0;
   PLO_TRY(plo_sort_pairs(c, keys, vals, m, kLsPasses, c->ls_hist.as<int>(), c->ls_tot.as<int>(), &which));
-  k_ls_select<<<gk, 256, 0, c->stream>>>(vals[which], c->state.as<DevState>(), adv, m, c->dprm.ls_threshold, c->ls_mask.as<int>());
+  k_ls_select<<<gk, 256, 0, c->stream>>>(vals[which], c->state.as<DevState>(), adv, m, c->dprm.ls_threshold, c->ls_mask.as<int>(),
+                                         in_unit);
+  P.weight_mode = PLO_W_UNIT;   // second pass: the mask is the selection
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                       c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
-                                                      c->partials.as<double>(), adv, c->ls_mask.as<int>());
+                                                      c->partials.as<double>(), adv, c->ls_mask.as<int>(), 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond, 2);

@@ -229,9 +229,11 @@ int plo_set_params(plo_ctx* c, const plo_params* p) {
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown weight_mode");
   if (p->solver != PLO_SOLVER_WLS && p->solver != PLO_SOLVER_LS && p->solver != PLO_SOLVER_RANSAC)
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: unknown solver");
-  if (p->solver == PLO_SOLVER_RANSAC && p->ransac_final != PLO_FINAL_WLS && p->ransac_final != PLO_FINAL_DRPM)
-    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_set_params: RANSAC final_solve_method must be Weighted LS or DRPM");
-  if (p->solver == PLO_SOLVER_LS && !(p->ls_threshold >= 0.0 && p->ls_threshold < 0.5))
+  if (p->solver == PLO_SOLVER_RANSAC && p->ransac_final != PLO_FINAL_LS && p->ransac_final != PLO_FINAL_WLS &&
+      p->ransac_final != PLO_FINAL_DRPM)
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_set_params: RANSAC final_solve_method must be LS, Weighted LS or DRPM");
+  const bool trims = p->solver == PLO_SOLVER_LS || (p->solver == PLO_SOLVER_RANSAC && p->ransac_final == PLO_FINAL_LS);
+  if (trims && !(p->ls_threshold >= 0.0 && p->ls_threshold < 0.5))
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_params: ls_threshold must be in [0, 0.5)");
   const bool pca_changed = c->prm.r_normal != p->r_normal || c->prm.search_number_normal != p->search_number_normal ||
                            c->prm.is_get_normals != p->is_get_normals;

@@ -80,12 +80,14 @@ def test_config_flattening_and_rejections(tmp_path):
     ref_default["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "DRPM"
     p = plo.config.params_from_config(ref_default)
     assert p.solver == 2 and p.ransac_final == 2 and p.drpm_threshold == 0.05
+    ref_default["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "LS"
+    assert plo.config.params_from_config(ref_default).ransac_final == 0
     for mutate, msg in [
         (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "plane_ICP"), "plane_ICP"),
         (lambda c: c["laser_odometry"]["matching_method"].__setitem__("method", "bogus"), "Invalid MATCHING_METHOD"),
         (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "Teaser"), "Teaser"),
         (lambda c: c["laser_odometry"]["solve_method"].__setitem__("method", "nope"), "Invalid SOLVE_METHOD"),
-        (lambda c: c["laser_odometry"]["solve_method"]["RANSAC"].__setitem__("final_solve_method", "LS"), "only final_solve_method"),
+        (lambda c: c["laser_odometry"]["solve_method"]["RANSAC"].__setitem__("final_solve_method", "QR"), "unknown final_solve_method"),
         (lambda c: c["laser_odometry"]["matching_method"]["IMLS"]["use_tensor_voting"].__setitem__("enabled", True), "tensor"),
         (lambda c: c.__setitem__("backend", "cpu"), "no CPU fallback"),
     ]:

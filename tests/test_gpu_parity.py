@@ -666,11 +666,12 @@ def test_trimmed_ls_solver(oracle_mod):
     assert np.abs(Tw - Tg).max() > 1e-7
 
 
-@pytest.mark.parametrize("final", [1, 2])
+@pytest.mark.parametrize("final", [0, 1, 2])
 def test_ransac_front_and_drpm_tail(oracle_mod, final):
     """"next" row of SURVEY.md §8f, rank 1 — the literal config.json default chain on the device:
     RANSAC (FPS-3 hypotheses seeded by xorshift64 instead of the reference's rand(), inlier count,
-    Huber/exp weights at the best hypothesis) then Weighted LS (final=1) or DRPM (final=2)."""
+    Huber/exp weights at the best hypothesis) then trimmed LS on the inliers (final=0, src/solver.cpp:366-371),
+    Weighted LS (final=1) or DRPM (final=2)."""
     pair = W.hdl64_pair(max_source=20000)
     kw = dict(solver=2, ransac_final=final)
     ctx, orc = _both(oracle_mod, pair.target, pair.source, **kw)
@@ -702,7 +703,7 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     # stepped driver with the reference's own config.json strings
     cfg = plo.config.load_config()
     cfg["laser_odometry"]["solve_method"]["method"] = "RANSAC"
-    cfg["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = "Weighted LS" if final == 1 else "DRPM"
+    cfg["laser_odometry"]["solve_method"]["RANSAC"]["final_solve_method"] = ["LS", "Weighted LS", "DRPM"][final]
     odo = plo.LaserOdometry(cfg, resident=False)
     odo.process_frame(pair.target)
     _, st = odo.process_frame(pair.source)
