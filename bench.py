@@ -359,6 +359,9 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{max(1, args.cpu_steps)} full registrations of the same workload (kd-tree build + {so['iters']} ICP "
                          f"iterations each), oracle -O3 + OpenMP over queries", "ms_per_scan": ms, **detail}
+        # the single-thread line next to the OpenMP one (the reference's own loop is sequential)
+        v1, ms1, _c1, _T1, _s1, _d1 = run_cpu(pair, 1, 0, threads=1)
+        cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "ms_per_scan": ms1, "sample": "1 full registration"}
         rot = float(np.arccos(np.clip((np.trace(T[:3, :3].T @ To[:3, :3]) - 1) / 2, -1, 1)))
         parity = {"pose_rot_err_rad": rot, "pose_trans_err_m": float(np.linalg.norm(T[:3, 3] - To[:3, 3])),
                   "iters_gpu": iters, "iters_cpu": int(so["iters"]), "pairs_gpu": int(st["pairs"]), "pairs_cpu": int(so["pairs"]),
