@@ -67,6 +67,10 @@ constexpr bool kUseCache = true;
 constexpr bool kUseCache = false;
 #endif
 constexpr int kCacheN = 64;        // cached candidate positions per query (two per lane)
+#ifndef PLO_BLOCK_RANGES
+#define PLO_BLOCK_RANGES 85        // percent of the source handed out as one contiguous range per block once the pose settles
+                                   // (0 = global counter only; 70 / 85 / 92 / 100 measured, profiles/r1j_ab_experiments.txt)
+#endif
 #ifndef PLO_CACHE_INFLATE
 #define PLO_CACHE_INFLATE 3.2f     // refresh walk: bound (squared) = this x the k-th distance of the bound's reference
 #endif
@@ -649,19 +653,48 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
   __shared__ double T[12];
   if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
+#if PLO_BLOCK_RANGES > 0
+  __shared__ int s_next;
+  if (threadIdx.x == 0) s_next = 0;
+#endif
   __syncthreads();
 
   // Each warp walks chunks of `chunk` consecutive source points (handed out dynamically, one
   // atomic per chunk: per-query cost varies a lot).  Correctness never depends on the order of
   // the source points, only the quality of the carry bound does.
+#if PLO_BLOCK_RANGES > 0
+  // Locality: the first PLO_BLOCK_RANGES % of the source is cut into one contiguous range per block, whose warps
+  // take chunks from a shared-memory counter -- the eight warps of a block then work on neighbouring scan points
+  // and share leaves and boxes in L1; the rest is handed out through the global counter and evens out the tail.
+  // Only once the pose is settling (short chunks, even cost per query): with the long chunks and the uneven cost of
+  // the first projections the ranges unbalance the blocks (measured: second projection 0.41 -> 0.49 ms).
+  const int n_static = warm ? (int)((long long)n_src * PLO_BLOCK_RANGES / 100) / chunk * chunk : 0;
+  const int per_block = ((n_static + (int)gridDim.x - 1) / (int)gridDim.x + chunk - 1) / chunk * chunk;
+  const int b0 = min((int)blockIdx.x * per_block, n_static), b1 = min(b0 + per_block, n_static);
+  bool own_range = true;
+#endif
   while (true) {
-   int c0 = 0;
+   int c0 = 0, c_end = n_src;
+#if PLO_BLOCK_RANGES > 0
+   if (own_range) {
+     if (lane == 0) c0 = b0 + atomicAdd(&s_next, 1) * chunk;
+     c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+     c_end = b1;
+     if (c0 >= b1) own_range = false;
+   }
+   if (!own_range) {
+     if (lane == 0) c0 = n_static + atomicAdd(chunk_counter, 1) * chunk;
+     c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+     c_end = n_src;
+   }
+#else
    if (lane == 0) c0 = atomicAdd(chunk_counter, 1) * chunk;
    c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+#endif
    if (c0 >= n_src) break;
    float carry_kf = CUDART_INF_F, carry_x = 0.f, carry_y = 0.f, carry_z = 0.f;
    int carry_pos = -1;   // lane j < k: position of the previous query's j-th neighbour (valid while carry_kf is finite)
-   const int c1 = min(c0 + chunk, n_src);
+   const int c1 = min(c0 + chunk, c_end);
    for (int qi = c0; qi < c1; ++qi) {
     const float4 p = __ldg(&sp[qi]);
     const float4 nf = __ldg(&sn[qi]);
