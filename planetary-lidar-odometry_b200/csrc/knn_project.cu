@@ -58,8 +58,14 @@
 
 namespace {
 
-constexpr int kCap = 128;          // candidate buffer entries per warp
-constexpr int kWarpsPerBlock = 8;
+#ifndef PLO_KCAP
+#define PLO_KCAP 120   // 16 warps x this scratch must fit the 48 KB of static shared memory
+#endif
+constexpr int kCap = PLO_KCAP;     // candidate buffer entries per warp
+#ifndef PLO_WARPS_PER_BLOCK
+#define PLO_WARPS_PER_BLOCK 16   // 2 blocks of 16 warps per SM: with block-local source ranges more warps share a neighbourhood in L1
+#endif                           // (4 x 8: 2.27 ms per registration, 8 x 4: 2.40 ms, 2 x 16: 2.22 ms)
+constexpr int kWarpsPerBlock = PLO_WARPS_PER_BLOCK;
 // Candidate cache: measured, NOT in the default build -- compile with -DPLO_CACHE to enable
 #ifdef PLO_CACHE
 constexpr bool kUseCache = true;
@@ -79,7 +85,7 @@ constexpr int kCacheN = 64;        // cached candidate positions per query (two 
 #endif
 constexpr int kGreedyLeaves = PLO_GREEDY_LEAVES;   // leaves examined by the greedy phase-A bound
 #ifndef PLO_MINB
-#define PLO_MINB 4
+#define PLO_MINB 2
 #endif
 
 // neighbour list: lane j (< k) holds the j-th best entry
