@@ -890,10 +890,12 @@ __device__ void smallest_eigvec3(double a00, double a01, double a02, double a11,
 
 // one warp per map point (sorted position): k_normal nearest within r_normal, no self
 // match (flags = SORT_RESULTS only, :414-416); D1: a normal exists iff all slots filled.
+constexpr int kPcaWarps = 8;   // its own block size: one search per map point, no block-local ranges to share
+
 template <int LEVELS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_pca_normals(const __grid_constant__ MapView m, DevParams P,
+__global__ void __launch_bounds__(kPcaWarps * 32) k_pca_normals(const __grid_constant__ MapView m, DevParams P,
                                                                     double* __restrict__ nrm_pca, int n_pad) {
-  __shared__ WarpScratch s_ws[kWarpsPerBlock];
+  __shared__ WarpScratch s_ws[kPcaWarps];
   WarpScratch& ws = s_ws[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -962,12 +964,12 @@ int plo_launch_pca_normals(plo_ctx* c) {
   const MapView mv = c->map_view();
   double* out = c->nrm_pca.as<double>();
   switch (c->n_levels) {
-    case 1: k_pca_normals<1><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
-    case 2: k_pca_normals<2><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
-    case 3: k_pca_normals<3><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
-    case 4: k_pca_normals<4><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
-    case 5: k_pca_normals<5><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
-    default: k_pca_normals<6><<<grid, kWarpsPerBlock * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 1: k_pca_normals<1><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 2: k_pca_normals<2><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 3: k_pca_normals<3><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 4: k_pca_normals<4><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    case 5: k_pca_normals<5><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
+    default: k_pca_normals<6><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, out, (int)c->n_pad_t); break;
   }
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
