@@ -338,6 +338,14 @@ def test_trimmed_ls_ransac_weights_drpm(oracle_mod):
     p = oracle_mod.default_params(solver=2, ransac_final=1)
     ok, Dr = oracle_mod.solve_ransac(s, d, n, p)
     assert ok and np.abs(Dr - oracle_mod.solve_wls(s[inl], d[inl], n[inl], w)).max() < 3e-2
+    # RANSAC -> "LS" tail (src/solver.cpp:366-371): trimmed LS on the inliers of the best hypothesis.  With a threshold
+    # no pair can fail, the inlier set is the whole list whatever hypothesis won: exactly the plain trimmed LS
+    p = oracle_mod.default_params(solver=2, ransac_final=0, ransac_distance_threshold=1e6)
+    ok, Dl = oracle_mod.solve_ransac(s, d, n, p)
+    assert ok and np.abs(Dl - oracle_mod.solve_ls(s, d, n, 0.02)).max() < 1e-12
+    # ... and at the default threshold it stays within centimetres of the trimmed LS on the T = I inliers
+    ok, Dl = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(solver=2, ransac_final=0))
+    assert ok and np.abs(Dl - oracle_mod.solve_ls(s[inl], d[inl], n[inl], 0.02)).max() < 3e-2
     # degenerate plane: DRPM damps the unobservable directions instead of blowing up
     rng = np.random.default_rng(2)
     sp = np.zeros((500, 3))
@@ -352,7 +360,8 @@ def test_huber_exp_weight_mode_and_solver_dispatch(oracle_mod):
     pair = W.hdl64_pair(max_source=2500, max_target=25000)
     res = {}
     for name, kw in {"unit": {}, "huber": {"weight_mode": 1}, "ls": {"solver": 1},
-                     "ransac_wls": {"solver": 2, "ransac_final": 1}, "ransac_drpm": {"solver": 2}}.items():
+                     "ransac_ls": {"solver": 2, "ransac_final": 0}, "ransac_wls": {"solver": 2, "ransac_final": 1},
+                     "ransac_drpm": {"solver": 2}}.items():
         o = oracle_mod.Oracle(oracle_mod.default_params(**kw))
         o.set_target(pair.target)
         o.set_source(pair.source)
