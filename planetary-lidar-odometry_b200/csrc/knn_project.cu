@@ -294,7 +294,7 @@ __device__ __forceinline__ void exact_distances(const MapView& m, WarpScratch& w
   __syncwarp();
 }
 
-// massive ties at the bound (e.g. > 96 coincident points): keep the exact k best of the buffer.
+// massive ties at the bound (more than kCap - 32 coincident points): keep the exact k best of the buffer.
 // Out of line: pathological inputs only.
 __device__ __noinline__ float exact_shrink(const MapView& m, WarpScratch* ws, int count, float qx, float qy, float qz, double r2,
                                            int allow_self, int k, float Df) {
