@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg5-sequences", type=int, default=64, help="BASELINE config 5: independent sequences sharded over the ranks (0 = skip)")
+    ap.add_argument("--cfg5-frames", type=int, default=21, help="frames per cfg-5 sequence (>= 2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly ONE JSON line: everything else that lands on fd 1 (NCCL's version banner, library
@@ -175,21 +177,26 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl_name = f"north-star: HDL-64 frame (~132k pts) vs {args.map_points}-pt local map, config.json defaults, weighted LS (unit weights)"
 
+    def config_block(n_s, n_t, iters, pairs):
+        # both arms emit exactly this key set (the driver compares the two lines' config)
+        return {"workload": wl_name, "source_points": int(n_s), "map_points": int(n_t), "iterations_to_converge": int(iters),
+                "pairs": int(pairs), "l2": "flushed between timed steps (256 MiB write)",
+                "parallelism": f"{world} independent registrations, one per GPU" if world > 1 else "single GPU", "seed": 1002}
+
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         pair = workload(1002, args.map_points)
         steps = max(1, args.steps)
-        v, ms, cores, T, st, detail = run_cpu(pair, steps, min(args.warmup, 1))
+        v, ms, cores, T, st, detail = run_cpu(pair, steps, args.warmup)
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "source_points": int(pair.source.shape[0]), "map_points": int(pair.target.shape[0]),
-                       "iterations_to_converge": int(st["iters"]),
-                       "note": "reference cannot be compiled here (Eigen/libnabo/PCL/ROS absent); this is the CPU oracle port "
-                               "of its algorithm, -O3 + OpenMP over queries"},
+            "config": config_block(pair.source.shape[0], pair.target.shape[0], st["iters"], st["pairs"]),
+            "note": "reference cannot be compiled here (Eigen/libnabo/PCL/ROS absent); this is the CPU oracle port of its "
+                    "algorithm, -O3 + OpenMP over queries; each step = one full registration of the same bytes as the GPU arm",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} full registrations (kd-tree build + {st['iters']} ICP iterations each)", **detail},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,6 +205,19 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    # BASELINE config 5: 64 independent VLP-32C sequences (seeds 5000..5063), sequence s -> rank s mod N.  The frames
+    # of this rank's shard are ray-cast here, in forked workers, BEFORE CUDA is initialised in this process.
+    cfg5_sets = None
+    cfg5_gen_s = 0.0
+    if args.cfg5_sequences > 0 and args.cfg5_frames >= 2:
+        import plo_b200 as _plo
+        seeds = list(range(5000, 5000 + args.cfg5_sequences))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        cfg5_sets = _plo.synth.workloads.generate_sequences(seeds, args.cfg5_frames,
+                                                            own=_plo.distributed.shard_units(len(seeds), rank, world),
+                                                            workers=max(1, cores // world))
+        cfg5_gen_s = time.perf_counter() - t0
     import torch
     import torch.distributed as dist
     import plo_b200 as plo
@@ -324,6 +344,36 @@ def main():
     assert np.array_equal(T2, T), "host-input and device-input paths disagree"
     assert all(np.array_equal(Tb[i], T) for i in range(args.steps)), "batched path disagrees"
 
+    # ---- BASELINE config 5: the 64 sequences, sharded over the ranks (strong scaling: total work fixed) ----
+    # every frame pair starts from the identity against the previous frame (src/laser_odometry.cpp:484-485, :116-136),
+    # poses chain as nowPose = prevLaserPose * rPose (:649-655); one all-gather of poses + stats ends the run.
+    # table_sha256 is over the gathered [units x 20] fp64 table: it must not depend on N.
+    cfg5 = None
+    if cfg5_sets is not None:
+        import hashlib
+        barrier()
+        tinfo = {}
+        t0 = time.perf_counter()
+        trajs, table = plo.distributed.register_sequences_sharded(ctx, cfg5_sets, device=dev, timing=tinfo)
+        torch.cuda.synchronize(dev)
+        t_cfg5 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_cfg5, tinfo["register_s"], tinfo["gather_ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_cfg5, tinfo["register_s"], tinfo["gather_ms"] = (float(x) for x in t.tolist())
+        n_pairs = sum(fs.n_frames - 1 for fs in cfg5_sets)
+        ate = []
+        for fs, tr in zip(cfg5_sets, trajs):     # trajectory error against the generator's ground truth
+            gt = np.stack([np.linalg.inv(fs.poses[0]) @ P for P in fs.poses])
+            ate.append(float(np.sqrt(np.mean(np.sum((tr[:, :3, 3] - gt[:, :3, 3]) ** 2, axis=1)))))
+        cfg5 = {"sequences": len(cfg5_sets), "frames": int(sum(fs.n_frames for fs in cfg5_sets)), "pairs": int(n_pairs),
+                "scans_per_s": n_pairs / t_cfg5, "seconds": t_cfg5, "register_s_max_rank": tinfo["register_s"],
+                "gather_ms": tinfo["gather_ms"], "table_sha256": hashlib.sha256(np.ascontiguousarray(table).tobytes()).hexdigest(),
+                "scaling": "strong", "sharding": "sequence s -> rank s mod N, one plo_register_batch per sequence from host frames",
+                "status_counts": {str(int(k)): int(v) for k, v in zip(*np.unique(table[:, 19], return_counts=True))},
+                "mean_iters": float(table[table[:, 16] > 0, 16].mean()), "ate_rmse_m_max": max(ate), "ate_rmse_m_mean": float(np.mean(ate)),
+                "frame_generation_s": cfg5_gen_s, "seeds": "5000.." + str(4999 + len(cfg5_sets))}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -363,18 +413,40 @@ def main():
         v1, ms1, _c1, _T1, _s1, _d1 = run_cpu(pair, 1, 0, threads=1)
         cpu["single_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "ms_per_scan": ms1, "sample": "1 full registration"}
         rot = float(np.arccos(np.clip((np.trace(T[:3, :3].T @ To[:3, :3]) - 1) / 2, -1, 1)))
-        parity = {"pose_rot_err_rad": rot, "pose_trans_err_m": float(np.linalg.norm(T[:3, 3] - To[:3, 3])),
+        # SURVEY 8d gates at the full size, first projection (identity pose): neighbour index arrays, IMLS heights,
+        # the six drop counters -- oracle vs CUDA path on the same bytes
+        import oracle_ctypes as oc
+        orc = oc.Oracle(threads=cores)
+        orc.set_target(pair.target)
+        orc.set_source(pair.source)
+        o0 = orc.project(np.eye(4), hooks=True)
+        ctx.set_target(d_tgt)
+        ctx.set_source(d_src)
+        g0 = ctx.project(np.eye(4), hooks=True)
+        nb0, q0 = ctx.neighbors(), ctx.query_results()
+        both = (o0["status"] == 0) & (q0["status"] == 0)
+        dI = np.abs(q0["height"][both] - o0["height"][both])
+        aI = np.abs(o0["height"][both])
+        gates = {"nn_mismatches": int((nb0["nn_idx"] != o0["nn_idx"]).sum()),
+                 "nn_d2_mismatches": int((nb0["nn_d2"] != o0["nn_d2"]).sum()),
+                 "status_mismatches": int((q0["status"] != o0["status"]).sum()),
+                 "imls_max_rel_err": float(np.max(dI / np.maximum(aI, 1e-12))) if dI.size else 0.0,
+                 "imls_max_abs_err_m": float(dI.max()) if dI.size else 0.0,
+                 "imls_within_1e-9_rel_plus_1e-12_abs": bool(np.all(dI <= 1e-9 * aI + 1e-12)),
+                 "drop_counters_equal": bool(np.array_equal(g0["counters"], o0["counters"])),
+                 "queries": int(q0["status"].shape[0]), "neighbour_slots": int(nb0["nn_idx"].size)}
+        del orc
+        parity = {**gates, "pose_rot_err_rad": rot, "pose_trans_err_m": float(np.linalg.norm(T[:3, 3] - To[:3, 3])),
                   "iters_gpu": iters, "iters_cpu": int(so["iters"]), "pairs_gpu": int(st["pairs"]), "pairs_cpu": int(so["pairs"]),
-                  "pass": bool(rot < 1e-5 and np.linalg.norm(T[:3, 3] - To[:3, 3]) < 1e-4 and iters == so["iters"])}
+                  "pass": bool(rot < 1e-5 and np.linalg.norm(T[:3, 3] - To[:3, 3]) < 1e-4 and iters == so["iters"]
+                               and gates["nn_mismatches"] == 0 and gates["status_mismatches"] == 0
+                               and gates["imls_within_1e-9_rel_plus_1e-12_abs"] and gates["drop_counters_equal"])}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "source_points": n_s, "map_points": n_t, "iterations_to_converge": iters,
-                   "pairs": int(st["pairs"]), "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": f"{world} independent registrations, one per GPU" if world > 1 else "single GPU",
-                   "seed": 1002},
+        "config": config_block(n_s, n_t, iters, st["pairs"]),
         "ms_per_icp_iteration": float(np.mean(reg_ms)) / max(iters, 1),
         "ms_index_build": float(np.mean(idx_ms)), "ms_register_loop": float(np.mean(reg_ms)),
         "gather_ms": gather_ms,
@@ -390,6 +462,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,
+        "cfg5": cfg5,
     }
     emit(line)
     if world > 1:

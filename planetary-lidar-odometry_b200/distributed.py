@@ -67,10 +67,14 @@ def chain_poses(rel: np.ndarray) -> np.ndarray:
     return out
 
 
-def register_sequences_sharded(ctx, sequences, device=None):
+def register_sequences_sharded(ctx, sequences, device=None, timing: dict | None = None):
     """cfg-5: `sequences` is a list of objects with n_frames / frame(k); each rank registers the
     frame pairs of its own sequences (one plo_register_batch per sequence) and all ranks end with
-    every sequence's global trajectory.  Returns list of [n_frames, 4, 4] arrays."""
+    every sequence's global trajectory.  Returns (list of [n_frames, 4, 4] arrays, result table).
+    `timing` (optional dict) receives `register_s` (this rank's registrations, host clock around the
+    batch calls, which synchronise) and `gather_ms` (the one collective)."""
+    import time
+
     import torch.distributed as dist
 
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -78,6 +82,7 @@ def register_sequences_sharded(ctx, sequences, device=None):
     offsets = np.cumsum([0] + [s.n_frames for s in sequences])
     n_units = int(offsets[-1])
     rows, units = [], []
+    t0 = time.perf_counter()
     for si in shard_units(len(sequences), rank, world):
         seq = sequences[si]
         frames = [seq.frame(k) for k in range(seq.n_frames)]
@@ -87,5 +92,11 @@ def register_sequences_sharded(ctx, sequences, device=None):
         for k in range(1, seq.n_frames):
             rows.append(pack_result(T[k - 1], st[k - 1]))
             units.append(int(offsets[si]) + k)
-    table = gather_results(np.asarray(rows).reshape(-1, RESULT_WIDTH), units, n_units, device=device)
+    t1 = time.perf_counter()
+    # every rank knows the largest shard (sequence lengths are global knowledge): ONE collective
+    slots = max(sum(sequences[si].n_frames for si in shard_units(len(sequences), r, world)) for r in range(world))
+    table = gather_results(np.asarray(rows).reshape(-1, RESULT_WIDTH), units, n_units, device=device, slots=slots)
+    if timing is not None:
+        timing["register_s"] = t1 - t0
+        timing["gather_ms"] = 1e3 * (time.perf_counter() - t1)
     return [chain_poses(table[offsets[i]:offsets[i + 1], :16].reshape(-1, 4, 4)) for i in range(len(sequences))], table

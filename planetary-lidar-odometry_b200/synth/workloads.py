@@ -196,3 +196,52 @@ def rigid_copy_pair(seed: int = 7, n: int = 4000, noise: float = 0.0) -> Pair:
     src[:, 0:3] = (p @ Ti[:3, :3].T + Ti[:3, 3]).astype(np.float32)
     src[:, 4:7] = (tgt[:, 4:7].astype(np.float64) @ Ti[:3, :3].T).astype(np.float32)
     return Pair("rigid_copy", src, tgt, T)
+
+
+# ---- materialised sequences (cfg-2 at length, cfg-5): frames generated once, in parallel ---------------
+
+class FrameSet:
+    """A sequence whose frames are already in memory (same interface as `Sequence`)."""
+
+    def __init__(self, seed: int, poses, frames=None):
+        self.seed = seed
+        self.poses = poses
+        self.n_frames = len(poses)
+        self._frames = frames          # list of (n, 12) float32 arrays, or None for a shard this process does not own
+
+    def frame(self, k: int) -> np.ndarray:
+        if self._frames is None:
+            raise RuntimeError(f"sequence {self.seed}: frames were not generated in this process (not its shard)")
+        return self._frames[k]
+
+    def relative_gt(self, k: int) -> np.ndarray:
+        return np.linalg.inv(self.poses[k - 1]) @ self.poses[k]
+
+
+def _gen_frame(job):
+    seed, n_frames, sensor, k = job
+    return Sequence(seed=seed, n_frames=n_frames, sensor=sensor).frame(k)
+
+
+def generate_sequences(seeds, n_frames: int, own=None, sensor: str = "vlp32c", workers: int = 0) -> list[FrameSet]:
+    """`FrameSet`s for `seeds`; frames are ray-cast (in `workers` forked processes) only for the indices in
+    `own` (default: all) — the other entries carry poses and length only.  Call before CUDA is initialised
+    in this process (fork).  Every frame is a pure function of (seed, k): identical bytes whatever the split."""
+    import multiprocessing as mp
+    import os
+    own = list(range(len(seeds))) if own is None else list(own)
+    jobs = [(seeds[i], n_frames, sensor, k) for i in own for k in range(n_frames)]
+    if workers <= 0:
+        workers = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(workers, len(jobs)))
+    if workers == 1 or not jobs:
+        frames = [_gen_frame(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            frames = pool.map(_gen_frame, jobs, chunksize=1)
+    out = []
+    it = iter(frames)
+    for i, s in enumerate(seeds):
+        poses = trajectory(n_frames, s)
+        out.append(FrameSet(s, poses, [next(it) for _ in range(n_frames)] if i in own else None))
+    return out

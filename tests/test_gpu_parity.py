@@ -495,6 +495,63 @@ def test_cfg2_vlp32c_sequence_full_size(oracle_mod):
         assert np.linalg.norm(st["rPose"][:3, 3] - gt[:3, 3]) < 0.05 and _rot_err(st["rPose"][:3, :3], gt[:3, :3]) < 5e-3
 
 
+def test_cfg2_sequence_201_frames_ate_tum_and_oracle_parity(oracle_mod, tmp_path):
+    """BASELINE config 2 at length: 201 full-size VLP-32C frames (200 registrations) through LaserOdometry on the
+    resident path.  Checked: (i) pose chaining nowPose = prevLaserPose * rPose (src/laser_odometry.cpp:649-655) over
+    200 products, bit for bit against a host-side product of the per-frame rPose; (ii) oracle pose / iteration /
+    pair-count parity on every 20th frame; (iii) every frame converges and stays close to the generator's ground-truth
+    motion, trajectory ATE (RMSE of positions, frame-0 coordinates) bounded; (iv) the TUM file of savePoseToFile
+    (src/saver.cpp:46-54: `timestamp tx ty tz qx qy qz qw`, 6 decimals) round-trips the trajectory."""
+    n = 201
+    fs = W.generate_sequences([2001], n)[0]
+    frames = [fs.frame(k) for k in range(n)]
+    assert all(40000 < f.shape[0] < 70000 for f in frames)
+    odo = plo.LaserOdometry(resident=True)
+    P = odo.run(frames)
+    assert P.shape == (n, 4, 4)
+    # (i) chaining
+    cur = np.eye(4)
+    for k in range(1, n):
+        cur = cur @ odo.frame_stats[k]["rPose"]
+        assert np.array_equal(cur, P[k])
+    # (ii) oracle parity on every 20th registration
+    orc = oracle_mod.Oracle()
+    for k in range(20, n, 20):
+        orc.set_target(frames[k - 1])
+        orc.set_source(frames[k])
+        To, so = orc.register()
+        st = odo.frame_stats[k]
+        assert st["iters"] == so["iters"] and st["status"] == so["status"] and st["pairs"] == so["pairs"], k
+        assert _rot_err(st["rPose"][:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(st["rPose"][:3, 3] - To[:3, 3]) < POSE_M, k
+    # (iii) ground truth
+    gt = np.stack([np.linalg.inv(fs.poses[0]) @ T for T in fs.poses])
+    for k in range(1, n):
+        st = odo.frame_stats[k]
+        assert st["status"] == 1, (k, st["status_name"])
+        rel = fs.relative_gt(k)
+        assert np.linalg.norm(st["rPose"][:3, 3] - rel[:3, 3]) < 0.05 and _rot_err(st["rPose"][:3, :3], rel[:3, :3]) < 5e-3, k
+    ate = float(np.sqrt(np.mean(np.sum((P[:, :3, 3] - gt[:, :3, 3]) ** 2, axis=1))))
+    path_len = float(np.sum(np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1)))
+    assert path_len > 100.0
+    assert ate < 0.01 * path_len, (ate, path_len)      # < 1 % of the distance travelled
+    # (iv) TUM output
+    out = str(tmp_path / "laser_odometry_poses.txt")
+    plo.save_poses_tum(out, P)
+    rows = np.loadtxt(out)
+    assert rows.shape == (n, 8)
+    lines = open(out, encoding="utf-8").read().splitlines()
+    assert all(len(f.split(".")[1]) == 6 for f in lines[7].split(" "))      # 6 decimals, every field
+    assert np.abs(rows[:, 1:4] - P[:, :3, 3]).max() <= 5.1e-7
+    q = rows[:, 4:8]     # qx qy qz qw -> rotation
+    assert np.abs(np.linalg.norm(q, axis=1) - 1.0).max() < 5e-6
+    for k in (0, 57, 200):
+        x, y, z, w = q[k]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(R - P[k, :3, :3]).max() < 5e-6      # 6-decimal quaternion components
+
+
 def test_cfg4_five_million_point_map(oracle_mod):
     """BASELINE config 4 (HDL-64 frame vs 5 M-point map: index build + radius-search stress, 4 tree levels):
     iteration-0 neighbour sets against the oracle on a query subset, full-loop pose parity, index-size properties."""
