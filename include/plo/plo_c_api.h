@@ -318,6 +318,12 @@ PLO_API int plo_last_timings(plo_ctx* ctx, float* ms_index_build, float* ms_regi
  * projection-kernel launch of the resident loop is bracketed by an event pair on the
  * context's stream.  plo_last_kernel_timings returns the mean device ms of the launches
  * that did work in the last plo_register and how many those were. */
+/* tuning / test knobs (no reference counterpart): "chunk" (consecutive source points per warp in k_project_cold, 0 =
+ * device-side policy; PLO_CHUNK in the environment at plo_create), "no_graph" (enqueue every iteration instead of the
+ * conditional CUDA graph: ncu cannot profile kernel nodes of such graphs; PLO_NO_GRAPH), "force_warm" (stepped
+ * projections start in the settled regime: candidate tiles are written and k_project_settled consumes them -- lets the
+ * parity tests exercise that kernel through plo_project). */
+PLO_API int plo_set_tuning(plo_ctx* ctx, const char* name, int32_t value);
 PLO_API int plo_set_profiling(plo_ctx* ctx, int32_t enabled);
 PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_t* n_project);
 /* the same launches one by one (ICP iteration i of the last plo_register -> ms_each[i], at most cap
@@ -325,6 +331,9 @@ PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_
 PLO_API int plo_last_project_times(plo_ctx* ctx, float* ms_each, int32_t cap, int32_t* n_project);
 /* per-kernel timing of one projection pass for the roofline: runs the projection kernel
  * `reps` times at the current pose and returns the mean device ms per launch */
+/* per projection of the last plo_register: how many queries k_project_settled could not answer from their candidate
+ * tile and handed to the tree walk (-1: the settled kernel did not run in that projection) */
+PLO_API int plo_last_tile_misses(plo_ctx* ctx, int32_t* misses, int32_t cap, int32_t* n_project);
 PLO_API int plo_time_project_kernel(plo_ctx* ctx, const double T[16], int32_t reps, float* ms_mean);
 
 #ifdef __cplusplus

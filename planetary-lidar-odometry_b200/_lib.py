@@ -76,6 +76,7 @@ EXPORTS = [
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
     "plo_last_kernel_timings", "plo_map_reset", "plo_map_push", "plo_map_push_device", "plo_map_info", "plo_map_get",
     "plo_frontend_default_params", "plo_frontend", "plo_frontend_device", "plo_frontend_get", "plo_frontend_device_records",
+    "plo_set_tuning", "plo_last_tile_misses",
 ]
 
 
@@ -105,6 +106,8 @@ def lib() -> C.CDLL:
     L.plo_last_error.restype = C.c_char_p
     L.plo_set_stream.argtypes = [vp, vp]
     L.plo_synchronize.argtypes = [vp]
+    L.plo_set_tuning.argtypes = [vp, C.c_char_p, i32]
+    L.plo_last_tile_misses.argtypes = [vp, vp, i32, C.POINTER(i32)]
     L.plo_default_params.argtypes = [C.POINTER(PloParams)]
     L.plo_default_params.restype = None
     L.plo_set_params.argtypes = [vp, C.POINTER(PloParams)]

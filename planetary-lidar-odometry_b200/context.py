@@ -83,6 +83,10 @@ class Context:
         self._ck(self.L.plo_set_stream(self.h, C.c_void_p(int(raw))))
         self._stream_keep = stream
 
+    def set_tuning(self, name: str, value: int):
+        """tuning / test knobs of plo_set_tuning: chunk, no_graph, force_warm"""
+        self._ck(self.L.plo_set_tuning(self.h, name.encode(), int(value)))
+
     def synchronize(self):
         self._ck(self.L.plo_synchronize(self.h))
 
@@ -323,6 +327,13 @@ class Context:
         n = C.c_int32()
         self._ck(self.L.plo_last_project_times(self.h, _ptr(ms), 64, C.byref(n)))
         return ms[: n.value].copy()
+
+    def last_tile_misses(self) -> np.ndarray:
+        """per projection of the last register(): queries the settled kernel handed to the tree walk (-1: it did not run)"""
+        out = np.zeros(32, np.int32)
+        n = C.c_int32()
+        self._ck(self.L.plo_last_tile_misses(self.h, _ptr(out), 32, C.byref(n)))
+        return out[: n.value].copy()
 
     def time_project_kernel(self, T=None, reps: int = 10) -> float:
         T = np.ascontiguousarray(np.eye(4) if T is None else T, dtype=np.float64).reshape(16)

@@ -394,13 +394,6 @@ __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ 
   }
 }
 
-// tile order of the source: slot t -> stripped index of the t-th point along the source's Hilbert curve
-__global__ void __launch_bounds__(256) k_source_order(const int* __restrict__ vals_sorted, const int* __restrict__ cidx, int n,
-                                                      int* __restrict__ order) {
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t < n) order[t] = cidx[vals_sorted[t]];
-}
-
 // ---- local map: TransformToEnd of src/laser_odometry.cpp:88-114 on the device ----
 
 struct MapPose { double m[12]; };   // rows of [R t]: x_prev = R x_cur + t (rPose of the registration just done)
@@ -606,48 +599,14 @@ int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t st
   PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * (size_t)(nb + 1)));
   cudaStream_t s = c->stream;
   const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
-  // PLO_PROJECT=tile selects the experimental lane-per-query kernel (knn_project_tile.cuh), which wants the queries
-  // of a warp spatially adjacent: the source is then ordered along its own Hilbert curve (10 bits per axis, 3 sort
-  // passes).  Measured slower than the warp-per-query kernel at 132 k queries, so it is opt-in.
-  {
-    const char* e = getenv("PLO_PROJECT");
-    c->tile_mode = e != nullptr && std::string(e) == "tile";
-  }
-  if (c->tile_mode) {
-    PLO_CUDA(c, c->s_bbox.reserve(sizeof(unsigned) * 8));
-    k_init_bbox<<<1, 32, 0, s>>>(c->s_bbox.as<unsigned>());
-    LAUNCH_CHECK(c);
-  }
   k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, vec16, c->s_praw.as<float4>(),
-                                    c->s_nraw.as<float4>(), c->blockcnt.as<int>(),
-                                    c->tile_mode ? c->s_bbox.as<unsigned>() : nullptr);
+                                    c->s_nraw.as<float4>(), c->blockcnt.as<int>(), nullptr);
   LAUNCH_CHECK(c);
   k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_source);
   LAUNCH_CHECK(c);
   k_compact_source<<<nb, 256, 0, s>>>(c->s_praw.as<float4>(), c->s_nraw.as<float4>(), (int)n, c->blockcnt.as<int>(),
                                       c->s_p.as<float4>(), c->s_n.as<float4>());
   LAUNCH_CHECK(c);
-  if (c->tile_mode) {
-    const int nbs = (int)((n + kSortTile - 1) / kSortTile);
-    PLO_CUDA(c, c->s_cidx.reserve(sizeof(int) * n));
-    PLO_CUDA(c, c->s_order.reserve(sizeof(int) * n));
-    for (int a = 0; a < 2; ++a) {
-      PLO_CUDA(c, c->keys[a].reserve(sizeof(unsigned long long) * n));
-      PLO_CUDA(c, c->vals[a].reserve(sizeof(int) * n));
-    }
-    PLO_CUDA(c, c->hist.reserve(sizeof(int) * (size_t)kRadix * nbs));
-    PLO_CUDA(c, c->digit_total.reserve(sizeof(int) * kPasses * kRadix));
-    k_keys<<<nb, 256, 0, s>>>(c->s_praw.as<float4>(), (int)n, c->blockcnt.as<int>(), c->s_bbox.as<unsigned>(),
-                              c->s_cidx.as<int>(), c->keys[0].as<unsigned long long>(), c->vals[0].as<int>());
-    LAUNCH_CHECK(c);
-    unsigned long long* kk[2] = {c->keys[0].as<unsigned long long>(), c->keys[1].as<unsigned long long>()};
-    int* vv[2] = {c->vals[0].as<int>(), c->vals[1].as<int>()};
-    int which = 0;
-    // key bits 10..39: the 10 most significant bits per axis (the non-finite sentinel has all 40 bits set)
-    PLO_TRY(plo_sort_pairs(c, kk, vv, n, 3, c->hist.as<int>(), c->digit_total.as<int>(), &which, kKeyBits - 3 * kRadixBits));
-    k_source_order<<<(int)((n + 255) / 256), 256, 0, s>>>(vv[which], c->s_cidx.as<int>(), (int)n, c->s_order.as<int>());
-    LAUNCH_CHECK(c);
-  }
   c->have_source = true;
   return PLO_OK;
 }

@@ -23,60 +23,11 @@
 
 #include "plo_internal.cuh"
 #include "plo_scan.cuh"
+#include "p2plane_device.cuh"
 
 namespace {
 
 constexpr int kReduceThreads = 256;
-
-__device__ __forceinline__ void ab_row(const double s[3], const double d[3], const double n[3], double a[6], double& b) {
-  // src/solver.cpp:185-192
-  a[0] = __dsub_rn(__dmul_rn(n[2], s[1]), __dmul_rn(n[1], s[2]));
-  a[1] = __dsub_rn(__dmul_rn(n[0], s[2]), __dmul_rn(n[2], s[0]));
-  a[2] = __dsub_rn(__dmul_rn(n[1], s[0]), __dmul_rn(n[0], s[1]));
-  a[3] = n[0]; a[4] = n[1]; a[5] = n[2];
-  b = __dadd_rn(__dadd_rn(__dmul_rn(n[0], __dsub_rn(d[0], s[0])), __dmul_rn(n[1], __dsub_rn(d[1], s[1]))),
-                __dmul_rn(n[2], __dsub_rn(d[2], s[2])));
-}
-
-__device__ __forceinline__ void apply_T3(const double* __restrict__ T, const double s[3], double out[3]) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    out[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[i * 4], s[0]), __dmul_rn(T[i * 4 + 1], s[1])), __dmul_rn(T[i * 4 + 2], s[2])), T[i * 4 + 3]);
-}
-
-// point-to-plane distance of a pair under hypothesis T (src/solver.cpp:306-307, :347-348)
-__device__ __forceinline__ double plane_distance(const double* __restrict__ T, const double s[3], const double d[3], const double n[3]) {
-  double tp[3];
-  apply_T3(T, s, tp);
-  return fabs(__dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(tp[0], d[0]), n[0]), __dmul_rn(__dsub_rn(tp[1], d[1]), n[1])),
-                        __dmul_rn(__dsub_rn(tp[2], d[2]), n[2])));
-}
-
-// RANSAC-final weight of src/solver.cpp:334-364 evaluated at hypothesis T (T_best of the RANSAC front,
-// or the identity for PLO_W_HUBER_EXP without RANSAC); < 0 => not an inlier
-__device__ __forceinline__ double huber_exp_weight(const double* __restrict__ T, const double s[3], const double d[3],
-                                                   const double n[3], const DevParams& P) {
-  const double dist = plane_distance(T, s, d, n);
-  if (!(dist < P.ransac_dist_thr)) return -1.0;
-  const double ar = exp(-dist);
-  const double sq = sqrt(ar);
-  return sq < P.huber_thr2 ? ar : 2.0 * P.huber_thr2 * sq - P.huber_thr2 * P.huber_thr2;
-}
-
-__device__ __forceinline__ void accumulate_pair(double acc[PLO_NSUM], const double s[3], const double d[3], const double n[3],
-                                                double w) {
-  double a[6], b;
-  ab_row(s, d, n, a, b);
-  int t = 0;
-#pragma unroll
-  for (int p = 0; p < 6; ++p)
-#pragma unroll
-    for (int q = p; q < 6; ++q) acc[t++] += w * a[p] * a[q];
-#pragma unroll
-  for (int p = 0; p < 6; ++p) acc[21 + p] += w * a[p] * b;
-  acc[27] += w;
-  acc[28] += w * b * b;
-}
 
 __device__ __forceinline__ void block_reduce_store(double acc[PLO_NSUM], double* __restrict__ partial) {
   __shared__ double s_red[kReduceThreads / 32][PLO_NSUM];
@@ -135,6 +86,70 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
   block_reduce_store(acc, partials + (size_t)blockIdx.x * PLO_NSUM);
 }
 
+// block partials -> s_sum (256 threads): value t is summed by warp (t mod 8), lane-strided partial sums in a fixed order,
+// fixed shuffle tree
+__device__ __forceinline__ void sum_block_partials(const double* __restrict__ partials, int n_partials, double* s_sum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < PLO_NSUM; t += 8) {
+    double v = 0.0;
+    for (int b = lane; b < n_partials; b += 32) v += __ldcg(&partials[(size_t)b * PLO_NSUM + t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PLO_FULL_MASK, v, o);
+    if (lane == 0) s_sum[t] = v;
+  }
+  __syncthreads();
+}
+
+// Resident weighted-LS loop: reduce + solve + loop tail in ONE launch.  Every block reduces its share of the pairs as
+// k_reduce_pairs does (same order, same partials); the last block to finish sums the block partials (fixed order),
+// solves and advances the loop state (k_solve_update, stage 0) -- bitwise the same result as the two stand-alone
+// kernels, one graph node and one dependent launch less per ICP iteration.
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const float4* __restrict__ qx, const float4* __restrict__ qy,
+                                                                 const float4* __restrict__ qn,
+                                                                 const DevCounts* __restrict__ counts, DevState* __restrict__ st,
+                                                                 DevParams P, double* __restrict__ partials,
+                                                                 int* __restrict__ done_ticket, cudaGraphConditionalHandle cond,
+                                                                 int use_cond) {
+  if (st->done) {
+    if (use_cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
+    return;
+  }
+  double acc[PLO_NSUM];
+#pragma unroll
+  for (int t = 0; t < PLO_NSUM; ++t) acc[t] = 0.0;
+  const int n_src = counts->n_source;
+  const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // the Huber/exp weights are evaluated at the identity
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+    const float4 x = __ldg(&qx[i]);
+    const int status = __float_as_int(x.w);
+    if (status != PLO_PT_OK) { acc[30 + status - 1] += 1.0; continue; }
+    const float4 y = __ldg(&qy[i]);
+    const float4 nn = __ldg(&qn[i]);
+    const double s[3] = {(double)x.x, (double)x.y, (double)x.z};
+    const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
+    const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
+    acc[29] += 1.0;
+    double w = 1.0;
+    if (P.weight_mode == PLO_W_HUBER_EXP) {
+      w = huber_exp_weight(I4, s, d, n, P);
+      if (w < 0.0) continue;
+    }
+    accumulate_pair(acc, s, d, n, w);
+  }
+  block_reduce_store(acc, partials + (size_t)blockIdx.x * PLO_NSUM);
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done_ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *done_ticket = 0;
+  __shared__ double s_sum[PLO_NSUM];
+  sum_block_partials(partials, (int)gridDim.x, s_sum);
+  if (threadIdx.x == 0) solve_from_sums(s_sum, st, P, 1, cond, use_cond, 0);
+}
+
 // reference-shaped inputs (n x 3 doubles each, optional weights) -> per-block partial sums
 __global__ void __launch_bounds__(kReduceThreads) k_reduce_host_pairs(const double* __restrict__ src, const double* __restrict__ ref,
                                                                       const double* __restrict__ nrm, const double* __restrict__ w,
@@ -150,91 +165,6 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_host_pairs(const doub
     accumulate_pair(acc, s, d, nn, w ? w[i] : 1.0);
   }
   block_reduce_store(acc, partials + (size_t)blockIdx.x * PLO_NSUM);
-}
-
-// ---- 6x6 solve + pose update (one thread) -------------------------------------------
-
-__device__ void rodrigues(const double r[3], double R[9]) {
-  // Eigen AngleAxisd(rot.norm(), rot.normalized()).toRotationMatrix(); a zero vector stays zero
-  const double z = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-  const double angle = sqrt(z);
-  double ax[3] = {r[0], r[1], r[2]};
-  if (z > 0.0) { ax[0] /= angle; ax[1] /= angle; ax[2] /= angle; }
-  const double sn = sin(angle), cs = cos(angle);
-  const double sa[3] = {sn * ax[0], sn * ax[1], sn * ax[2]};
-  const double ca[3] = {(1.0 - cs) * ax[0], (1.0 - cs) * ax[1], (1.0 - cs) * ax[2]};
-  double tmp;
-  tmp = ca[0] * ax[1]; R[1] = tmp - sa[2]; R[3] = tmp + sa[2];
-  tmp = ca[0] * ax[2]; R[2] = tmp + sa[1]; R[6] = tmp - sa[1];
-  tmp = ca[1] * ax[2]; R[5] = tmp - sa[0]; R[7] = tmp + sa[0];
-  R[0] = ca[0] * ax[0] + cs; R[4] = ca[1] * ax[1] + cs; R[8] = ca[2] * ax[2] + cs;
-}
-
-// orthogonal polar factor of a near-rotation (== U V^T of its SVD, src/solver.cpp:207-213):
-// Newton iteration X <- (X + X^-T) / 2, quadratically convergent
-__device__ void polar_orthogonalize(double R[9]) {
-  for (int it = 0; it < 4; ++it) {
-    const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
-    const double c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
-    const double c20 = R[1] * R[5] - R[2] * R[4], c21 = R[2] * R[3] - R[0] * R[5], c22 = R[0] * R[4] - R[1] * R[3];
-    const double det = R[0] * c00 + R[1] * c01 + R[2] * c02;
-    if (!(fabs(det) > 1e-300)) return;
-    const double id = 1.0 / det;   // X^-T = cofactor matrix / det
-    const double C[9] = {c00 * id, c01 * id, c02 * id, c10 * id, c11 * id, c12 * id, c20 * id, c21 * id, c22 * id};
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = 0.5 * (R[i] + C[i]);
-  }
-}
-
-// diagonally pivoted LDL^T solve of H x = g; returns the number of pivots used.
-// A pivot is dropped when the remaining diagonal is below (max|H_jj| * eps^2) * (cnt-k)/cnt,
-// the squared form of Eigen's ColPivHouseholderQR threshold_helper test (H_jj = |col j|^2).
-// x must NOT live on the caller's stack: inlined into k_solve_update, nvcc 12.9 let a local x[] share a stack slot
-// with A[][] (wrong results); the callers pass a shared-memory array.
-__device__ __forceinline__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
-  double A[6][6];
-  int t = 0;
-  for (int p = 0; p < 6; ++p)
-    for (int q = p; q < 6; ++q) { A[p][q] = H21[t]; A[q][p] = H21[t]; ++t; }
-  int perm[6] = {0, 1, 2, 3, 4, 5};
-  double rhs[6];
-  for (int i = 0; i < 6; ++i) rhs[i] = g[i];
-  double hmax = 0.0;
-  for (int i = 0; i < 6; ++i) hmax = fmax(hmax, A[i][i]);
-  const double helper = (hmax * DBL_EPSILON) * DBL_EPSILON / fmax(count, 1.0);
-  int rank = 6;
-  for (int k = 0; k < 6; ++k) {
-    int piv = k;
-    for (int j = k + 1; j < 6; ++j) if (A[j][j] > A[piv][piv]) piv = j;
-    const double dk = A[piv][piv];
-    if (!(dk > 0.0) || dk < helper * (count - k)) { rank = k; break; }
-    if (piv != k) {
-      for (int j = 0; j < 6; ++j) { const double tmp = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = tmp; }
-      for (int j = 0; j < 6; ++j) { const double tmp = A[j][k]; A[j][k] = A[j][piv]; A[j][piv] = tmp; }
-      const double tr = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = tr;
-      const int tp = perm[k]; perm[k] = perm[piv]; perm[piv] = tp;
-    }
-    for (int i = k + 1; i < 6; ++i) {
-      const double lik = A[k][i] / dk;   // row k stays unscaled (A[k][i] == a_ik), column k becomes L
-      for (int j = k + 1; j <= i; ++j) { A[i][j] -= lik * A[k][j]; A[j][i] = A[i][j]; }
-      A[i][k] = lik;
-    }
-  }
-  for (int i = 0; i < 6; ++i) x[i] = 0.0;
-  double y[6];
-  for (int i = 0; i < rank; ++i) {          // L z = rhs
-    double sacc = rhs[i];
-    for (int j = 0; j < i; ++j) sacc -= A[i][j] * y[j];
-    y[i] = sacc;
-  }
-  for (int i = 0; i < rank; ++i) y[i] /= A[i][i];   // D
-  for (int i = rank - 1; i >= 0; --i) {     // L^T x = y
-    double sacc = y[i];
-    for (int j = i + 1; j < rank; ++j) sacc -= A[j][i] * y[j];
-    y[i] = sacc;
-  }
-  for (int i = 0; i < rank; ++i) x[perm[i]] = y[i];
-  return rank;
 }
 
 // Eigen::ColPivHouseholderQR::solve for the 3 x 6 hypothesis system of src/solver.cpp:251-273 (basic
@@ -400,49 +330,6 @@ __global__ void __launch_bounds__(32) k_drpm_eigen(DevState* __restrict__ st, De
   }
 }
 
-// x -> deltaTrans (src/solver.cpp:203-217): Rodrigues, orthogonal polar factor, translation
-__device__ void delta_from_x(const double x[6], double D[16]) {
-  double R[9];
-  rodrigues(x, R);
-  polar_orthogonalize(R);
-  const double Dl[16] = {R[0], R[1], R[2], x[3], R[3], R[4], R[5], x[4], R[6], R[7], R[8], x[5], 0.0, 0.0, 0.0, 1.0};
-  for (int i = 0; i < 16; ++i) D[i] = Dl[i];
-}
-
-// tail of one loop iteration (one thread): delta, rPose = delta * rPose (src/laser_odometry.cpp:619),
-// convergence test (:628-646), loop condition of the resident graph
-__device__ void finish_iteration(DevState* __restrict__ st, const DevParams& P, const double x[6], int rank, int advance_loop,
-                                 cudaGraphConditionalHandle cond, int use_cond) {
-  st->rank = rank;
-  double D[16];
-  delta_from_x(x, D);
-  for (int i = 0; i < 16; ++i) st->delta[i] = D[i];
-  const double dd = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);   // :628-632
-  double ct = ((D[0] + D[5] + D[10]) - 1.0) / 2.0;                   // :636-638
-  ct = fmin(1.0, fmax(ct, -1.0));
-  const double da = acos(ct);
-  st->delta_dist = dd;
-  st->delta_angle = da;
-  if (!advance_loop) return;
-  double nP[16];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      double sacc = 0.0;
-      for (int k = 0; k < 4; ++k) sacc += D[i * 4 + k] * st->rPose[k * 4 + j];
-      nP[i * 4 + j] = sacc;
-    }
-  for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
-  st->iters += 1;
-  st->use_prev = 1;   // the projection just consumed left its k-th distances behind
-  // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
-  // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
-  st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
-  st->warm = (dd < 0.05 && da < 0.01) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
-  if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
-  else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
-  if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
-}
-
 __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__ partials, int n_partials, DevState* __restrict__ st,
                                                        DevParams P, int advance_loop, cudaGraphConditionalHandle cond, int use_cond,
                                                        int stage) {
@@ -455,51 +342,9 @@ __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__
     return;
   }
   __shared__ double s_sum[PLO_NSUM];
-  {
-    // value t is summed by warp (t mod 8): lane-strided partial sums in a fixed order, fixed shuffle tree
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = warp; t < PLO_NSUM; t += 8) {
-      double v = 0.0;
-      for (int b = lane; b < n_partials; b += 32) v += partials[(size_t)b * PLO_NSUM + t];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PLO_FULL_MASK, v, o);
-      if (lane == 0) s_sum[t] = v;
-    }
-  }
-  __syncthreads();
+  sum_block_partials(partials, n_partials, s_sum);
   if (threadIdx.x != 0) return;
-  const double count = s_sum[29];
-  double sw = s_sum[27];
-  for (int i = 0; i < 21; ++i) st->H[i] = s_sum[i];
-  for (int i = 0; i < 6; ++i) st->g[i] = s_sum[21 + i];
-  st->sw = sw;
-  st->swbb = s_sum[28];
-  if (stage != 2) {   // the statistics describe the projection, not the trimmed subset
-    st->pairs = (long long)count;
-    for (int i = 0; i < 6; ++i) st->dropped[i] = (long long)s_sum[30 + i];
-    st->rms = count > 0.0 ? sqrt(s_sum[28] / fmax(sw, 1e-300)) : 0.0;
-  }
-  if (advance_loop && count < (double)P.correspond_number) {   // src/laser_odometry.cpp:570-576
-    st->status = PLO_REG_TOO_FEW_PAIRS;
-    st->done = 1;
-    if (use_cond) cudaGraphSetConditional(cond, 0);
-    return;
-  }
-  double H[21], g[6];
-  // weights are normalised to sum 1 in the reference (src/solver.cpp:361-364); same argmin
-  const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
-  for (int i = 0; i < 21; ++i) H[i] = s_sum[i] * scale;
-  for (int i = 0; i < 6; ++i) g[i] = s_sum[21 + i] * scale;
-  if (stage == 3) return;   // DRPM: the sums are in the state; k_drpm_eigen / k_drpm_noise / k_drpm_finish go on
-  __shared__ double x[6];   // see solve_ldlt6
-  const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
-  if (stage == 1) {
-    st->rank = rank;
-    for (int i = 0; i < 6; ++i) st->x0[i] = x[i];
-    return;   // the loop condition keeps its value (1): the body goes on with the selection
-  }
-  for (int i = 0; i < 6; ++i) st->probs[i] = 0.0;
-  finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
+  solve_from_sums(s_sum, st, P, advance_loop, cond, use_cond, stage);
 }
 
 // ---- RANSAC front (src/solver.cpp:238-326) on the compacted pairs, one block --------------------
@@ -860,8 +705,9 @@ __global__ void __launch_bounds__(256) k_ls_select(const int* __restrict__ vals_
     mask[vals_sorted[j]] = (j >= lower && j <= upper) ? 1 : 0;
 }
 
-__global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
+__global__ void k_init_state(DevState* st, const double* T0, int use_prev, int force_warm) {
   if (threadIdx.x == 0) {
+    const int tiles_ready = use_prev ? st->tiles_ready : 0;   // tiles outlive a registration of the same clouds
     for (int i = 0; i < 16; ++i) {
       const double id = (i % 5 == 0) ? 1.0 : 0.0;
       st->rPose[i] = T0 ? T0[i] : id;
@@ -882,7 +728,9 @@ __global__ void k_init_state(DevState* st, const double* T0, int use_prev) {
     st->done = 0;
     st->use_prev = use_prev;
     st->chunk = use_prev ? PLO_CHUNK_MID : PLO_CHUNK_COLD;
-    st->warm = 0;
+    st->warm = force_warm;
+    st->tiles_ready = tiles_ready;
+    for (int i = 0; i < 32; ++i) st->miss_hist[i] = -1;
   }
 }
 
@@ -954,7 +802,7 @@ int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null) {
     PLO_CUDA(c, cudaMemcpyAsync(c->scratch.p, T0_host_or_null, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
     dT0 = c->scratch.as<double>();
   }
-  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0, c->prev_valid ? 1 : 0);
+  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0, c->prev_valid ? 1 : 0, c->tune_force_warm ? 1 : 0);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
@@ -964,6 +812,10 @@ constexpr int kLsPasses = 7;   // 64-bit keys, 10-bit digits
 
 int plo_reserve_solver_buffers(plo_ctx* c) {
   PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, 2)));
+  if (!c->reduce_ticket.p) {
+    PLO_CUDA(c, c->reduce_ticket.reserve(sizeof(int)));
+    PLO_CUDA(c, cudaMemsetAsync(c->reduce_ticket.p, 0, sizeof(int), c->stream));
+  }
   const bool trims = c->dprm.solver == PLO_SOLVER_LS || (c->dprm.solver == PLO_SOLVER_RANSAC && c->dprm.ransac_final == PLO_FINAL_LS);
   if (trims && c->m_raw > 0) {
     const size_t m = (size_t)c->m_raw;
@@ -1010,6 +862,16 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
                                         c->state.as<DevState>(), P, c->ransac_mind.as<double>(), adv);
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
+  }
+  if (advance_loop && c->tune_fuse && c->dprm.solver == PLO_SOLVER_WLS) {
+    // resident weighted-LS loop: one launch (k_reduce_pairs and k_solve_update read the qx / qy / qn a projection wrote
+    // in the same kernel; the projection itself may come through the read-only path here: another launch wrote it)
+    k_reduce_solve<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
+                                                        c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
+                                                        c->partials.as<double>(), c->reduce_ticket.as<int>(), cond, use_cond);
+    c->launches++;
+    PLO_CUDA(c, cudaGetLastError());
+    return PLO_OK;
   }
   if (c->m_raw > 0) {
     k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),

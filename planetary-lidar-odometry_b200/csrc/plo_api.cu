@@ -158,6 +158,10 @@ int plo_create(int device, plo_ctx** out) {
     return PLO_ERR_UNSUPPORTED;
   }
   c->sm_count = prop.multiProcessorCount;
+  // tuning knobs from the environment, read once (plo_set_tuning overrides them later)
+  if (const char* e = getenv("PLO_CHUNK")) c->tune_chunk = std::max(0, atoi(e));
+  if (const char* e = getenv("PLO_NO_GRAPH")) c->tune_no_graph = atoi(e) != 0;
+  if (const char* e = getenv("PLO_FUSE")) c->tune_fuse = atoi(e) != 0;
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   for (int i = 0; i < 4; ++i) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
@@ -179,9 +183,9 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->s_cidx, &c->s_bbox, &c->s_order, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_cache_pos, &c->q_cache_cx,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
-                    &c->counts, &c->scratch, &c->chunk_counter, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
+                    &c->counts, &c->scratch, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
   if (c->h_state) cudaFreeHost(c->h_state);
@@ -206,6 +210,17 @@ int plo_set_stream(plo_ctx* c, void* cuda_stream) {
   destroy_loop_graph(c);
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
+  return PLO_OK;
+}
+
+int plo_set_tuning(plo_ctx* c, const char* name, int32_t value) {
+  if (!c || !name) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: NULL argument");
+  const std::string n(name);
+  if (n == "chunk") c->tune_chunk = value;
+  else if (n == "no_graph") c->tune_no_graph = value != 0;
+  else if (n == "force_warm") c->tune_force_warm = value != 0;
+  else if (n == "fuse") c->tune_fuse = value != 0;
+  else return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: unknown knob '" + n + "' (chunk, no_graph, force_warm, fuse)");
   return PLO_OK;
 }
 
@@ -660,9 +675,9 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   add(c->stream);
   add(c->pts_sorted.p); add(c->nrm_sorted.p); add(c->nrm_pca.p);
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
-  add(c->s_order.p); v.push_back(c->tile_mode ? 1ull : 0ull);
-  add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p); add(c->q_cache_pos.p); add(c->q_cache_cx.p);
-  add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->chunk_counter.p);
+  add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p); add(c->q_tile_pts.p); add(c->q_tile_meta.p);
+  add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->sync_counters.p); add(c->miss_list.p); add(c->reduce_ticket.p);
+  v.push_back((unsigned long long)c->tune_chunk); v.push_back(c->tune_fuse ? 1ull : 0ull);
   add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);
   add(c->ransac_mind.p); add(c->partials2.p); add(c->h_src.p); add(c->h_ref.p); add(c->h_nrm.p); add(c->h_w.p); add(c->blockcnt.p);
   v.push_back((unsigned long long)c->n_levels);
@@ -681,8 +696,9 @@ static void destroy_loop_graph(plo_ctx* c) {
   c->loop_sig.clear();
 }
 
-// WHILE conditional node whose body is one ICP iteration (chunk-counter reset, k_project,
-// k_reduce_pairs, k_solve_update); k_solve_update sets the condition from the device-side state.
+// WHILE conditional node whose body is one ICP iteration: k_project_settled + the two k_project_cold instantiations,
+// then k_reduce_solve, whose last block solves and sets the condition from the device-side state (weighted LS); for
+// the other solvers the stand-alone reduce / solve kernels of p2plane_solve.cu follow and the last of them sets it.
 static int build_loop_graph(plo_ctx* c) {
   destroy_loop_graph(c);
   cudaGraph_t g = nullptr;
@@ -720,7 +736,6 @@ static int build_loop_graph(plo_ctx* c) {
 static int enqueue_register(plo_ctx* c, const double* T0) {
   PLO_TRY(plo_reserve_query_buffers(c, false));
   PLO_TRY(plo_reserve_solver_buffers(c));
-  PLO_CUDA(c, c->chunk_counter.reserve(sizeof(int)));
   if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
   PLO_TRY(plo_launch_init_state(c, T0));
   if (c->prm.iterations <= 0) { c->hooks_valid = false; return PLO_OK; }
@@ -729,8 +744,7 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
   // driver refuses conditional nodes) every iteration is enqueued up front instead; kernels of
   // iterations after convergence then see the device-side `done` flag and return at once.
   // PLO_NO_GRAPH=1: enqueue-all path (ncu cannot profile kernel nodes of graphs with conditional nodes)
-  static const bool no_graph_env = getenv("PLO_NO_GRAPH") != nullptr && atoi(getenv("PLO_NO_GRAPH")) != 0;
-  if (!c->profiling && c->graph_ok && !no_graph_env && c->m_raw > 0) {
+  if (!c->profiling && c->graph_ok && !c->tune_no_graph && c->m_raw > 0) {
     if (!c->loop_exec || c->loop_sig != loop_signature(c)) {
       if (build_loop_graph(c) != 0) c->graph_ok = false;
     }
@@ -937,6 +951,15 @@ int plo_last_timings(plo_ctx* c, float* ms_index_build, float* ms_register) {
   if (c->ev_reg_pending) { cudaEventElapsedTime(&c->ms_register, c->ev[2], c->ev[3]); c->ev_reg_pending = false; }
   if (ms_index_build) *ms_index_build = c->ms_index;
   if (ms_register) *ms_register = c->ms_register;
+  return PLO_OK;
+}
+
+int plo_last_tile_misses(plo_ctx* c, int32_t* misses, int32_t cap, int32_t* n_project) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  const int n = std::min(c->h_state->iters + (c->h_state->status == PLO_REG_TOO_FEW_PAIRS ? 1 : 0), 32);
+  if (misses)
+    for (int i = 0; i < n && i < cap; ++i) misses[i] = c->h_state->miss_hist[i];
+  if (n_project) *n_project = n;
   return PLO_OK;
 }
 

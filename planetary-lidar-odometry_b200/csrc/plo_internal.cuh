@@ -70,8 +70,9 @@ struct DevState {
   int done;       // kernels of later iterations return immediately when set
   int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds (temporal bound usable)
   int chunk;      // consecutive source points per warp in the next projection (carry bound vs. balance)
-  int warm;       // the last pose step was small: the next projection's queries barely move (candidate cache pays)
-  int pad1;
+  int warm;       // the last pose step was small: the next projection's queries barely move (short chunks, tiles are left behind)
+  int miss_hist[32];   // per projection of this registration: queries k_project_settled handed to the tree (-1: it did not run)
+  int tiles_ready; // every query has a candidate tile (or an invalid mark) from a projection of the same clouds: k_project_settled runs
 };
 
 struct DevCounts {
@@ -136,8 +137,6 @@ struct plo_ctx {
   int64_t m_raw = 0;
   bool have_source = false;
   DevBuf s_stage, s_stage2, s_praw, s_nraw, s_p, s_n;
-  DevBuf s_cidx, s_bbox, s_order;   // tile kernel: stripped index of every raw point, bounding box, Hilbert order
-  bool tile_mode = false;           // the source is large enough for the lane-per-query kernel (s_order valid)
 
   // device-resident local map (plo_map_push): frames back to back as 32-byte records {x,y,z,-,nx,ny,nz,-},
   // all expressed in the frame of the most recent push; two buffers, swapped on every push
@@ -153,14 +152,16 @@ struct plo_ctx {
 
   // per-query results of the last projection
   DevBuf q_x, q_y, q_n, q_status, q_kd2;
-  DevBuf q_cache_pos, q_cache_cx;   // per-query candidate cache of k_project (knn_project.cu header)
+  DevBuf q_tile_pts, q_tile_meta;   // per-query candidate tiles (knn_search.cuh): 64 x float4 + x_ref / e2
+  // one projection's device-side bookkeeping (knn_project.cu): counters, the settled kernel's miss list
+  DevBuf sync_counters, miss_list;
   bool prev_valid = false;   // q_x / q_kd2 hold the previous projection of the SAME clouds and k, r
   bool hooks_valid = false;
   DevBuf q_height, q_nn1_idx, q_nn1_d2, q_nn_idx, q_nn_d2, q_stats;
   bool projected = false;
 
   // reduction / solve
-  DevBuf partials, state, counts, scratch, chunk_counter;
+  DevBuf partials, state, counts, scratch, reduce_ticket;
   DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
   DevBuf ransac_mind, partials2;                              // RANSAC FPS distances, DRPM noise partials
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
@@ -177,7 +178,12 @@ struct plo_ctx {
   // batched mode: host->device copies of pair i+1 overlap the registration of pair i
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_batch_start = nullptr;
-  int body_launches = 3;   // kernels per loop iteration of the captured body
+  int body_launches = 2;   // kernels per loop iteration of the captured body
+  // tuning knobs: environment read once at plo_create (PLO_CHUNK, PLO_NO_GRAPH), or plo_set_tuning
+  int tune_chunk = -1;       // >= 0: chunk length of k_project_cold (0 = device-side policy)
+  bool tune_no_graph = false;   // enqueue-all loop instead of the conditional graph (ncu cannot profile kernel nodes of such graphs)
+  bool tune_fuse = true;        // resident weighted-LS loop: reduce + solve + loop tail in one launch (PLO_FUSE=0: the two stand-alone kernels)
+  bool tune_force_warm = false; // projections start in the settled regime (tiles stored / used) -- parity tests of k_project_settled
   bool graph_launched = false;   // the last enqueue_register went through the graph
   bool graph_ok = true;      // cleared if the driver rejects conditional nodes: falls back to enqueue-all
   bool profiling = false;

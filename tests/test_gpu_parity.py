@@ -767,25 +767,52 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
 
 
-def test_tile_kernel_parity(oracle_mod, monkeypatch):
-    """PLO_PROJECT=tile: the experimental lane-per-query projection kernel (csrc/knn_project_tile.cuh) is held to
-    the same bars as the default one — neighbour sets, d2, statuses, drop counters bit-exact, heights to tolerance,
-    the resident loop to the pose tolerance — on an urban pair, ragged sizes, coincident points and NaN inputs."""
-    monkeypatch.setenv("PLO_PROJECT", "tile")
+def test_settled_kernel_parity_from_candidate_tiles(oracle_mod):
+    """k_project_settled (the streaming kernel of the settled iterations) is held to the same bars as the tree walk:
+    with the `force_warm` knob a stepped projection leaves candidate tiles behind and the next ones consume them.
+    Small moves (tile hits), a move too large for most tiles (misses go to the tree through the miss list), a map of
+    quantised points (ties at the bound, ties by index), coincident points (second search of the 1-NN rule), k = 32,
+    ragged sizes, non-finite inputs: neighbour sets, d2, statuses, counters bit-exact, heights to tolerance."""
+    P = plo.synth.scenes.pose_matrix
     pair = W.hdl64_pair(max_source=20000)
     ctx, orc = _both(oracle_mod, pair.target, pair.source)
-    _check_projection(ctx, orc)
-    _check_projection(ctx, orc, T=pair.T_gt)            # second projection: temporal bounds in play
+    ctx.set_tuning("force_warm", 1)
+    _check_projection(ctx, orc, T=pair.T_gt)                       # tree walk, leaves the tiles
+    hits = []
+    for T in (P([0.002, -0.001, 0.0005], yaw_deg=0.01) @ pair.T_gt,            # mm moves: nearly every tile covers its bound
+              P([0.004, 0.001, -0.001], yaw_deg=-0.02, pitch_deg=0.01) @ pair.T_gt,
+              P([0.03, -0.02, 0.005], yaw_deg=0.1) @ pair.T_gt,                # cm move: dense regions miss, sparse ones hit
+              P([0.5, 0.2, 0.0], yaw_deg=2.0) @ pair.T_gt,                     # a jump: (nearly) everything goes to the tree
+              pair.T_gt):
+        _check_projection(ctx, orc, T=T)
+        hits.append(float((ctx.search_stats()[:, 2] % 100000 >= 50000).mean()))
+    # the settled kernel really answered these (the first walk had no temporal reference: its chunk heads left tight tiles)
+    assert hits[0] > 0.5 and hits[1] > 0.85, hits
+    assert 0.02 < hits[2] < 0.98 and hits[3] < 0.2, hits           # both kernels shared the third, the tree took the fourth
+    ctx.close()
+    # the resident loop on the same pair: tiles come into play from the fourth projection on
+    ctx, orc = _both(oracle_mod, pair.target, pair.source)
     Tg, sg = ctx.register()
     To, so = orc.register()
     assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"]
+    assert np.array_equal(sg["counters"], so["counters"])
     assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    Tg2, sg2 = ctx.register()                                     # same clouds again: starts with tiles and temporal bounds
+    assert np.array_equal(Tg, Tg2) and sg["iters"] == sg2["iters"]
+    ctx.close()
+    # k = 32, other radii
     ctx2, orc2 = _both(oracle_mod, pair.target[::3], pair.source[::10], search_number=32, r=1.5, h=0.7)
+    ctx2.set_tuning("force_warm", 1)
     _check_projection(ctx2, orc2)
+    _check_projection(ctx2, orc2, T=P([0.003, 0.0, 0.001]))
+    _check_projection(ctx2, orc2, T=P([0.006, 0.002, 0.0], yaw_deg=0.02))
+    ctx2.close()
     rng = np.random.default_rng(77)
-    for n_t, n_s in ((1, 1), (31, 7), (33, 64), (1025, 100), (5000, 333)):
+    for n_t, n_s in ((1, 1), (31, 7), (33, 64), (1025, 100), (5000, 333), (20000, 3000)):
         tgt = np.zeros((n_t, 12), np.float32)
         tgt[:, 0:3] = rng.uniform(-2, 2, size=(n_t, 3))
+        if n_t == 20000:
+            tgt[:, 0:3] = np.round(tgt[:, 0:3] * 8) / 8    # quantised map: many bit-equal distances, duplicates
         tgt[:, 4:7] = [0, 0, 1]
         src = np.zeros((n_s, 12), np.float32)
         src[:, 0:3] = rng.uniform(-2, 2, size=(n_s, 3))
@@ -797,7 +824,12 @@ def test_tile_kernel_parity(oracle_mod, monkeypatch):
             tgt[100:160, 0:3] = tgt[100, 0:3]            # 60 coincident map points: ties by index, 1-NN fallback
             src[11, 0:3] = tgt[100, 0:3]
         c3, o3 = _both(oracle_mod, tgt, src)
+        c3.set_tuning("force_warm", 1)
         _check_projection(c3, o3)
+        _check_projection(c3, o3)                        # same pose again: every valid tile hits
+        _check_projection(c3, o3, T=P([0.001, -0.001, 0.0005]))
+        _check_projection(c3, o3, T=P([0.0, 0.0, 0.0]))
+        c3.close()
 
 
 def test_local_map_transform_is_bit_exact_and_drops_oldest(oracle_mod):

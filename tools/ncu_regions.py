@@ -32,35 +32,36 @@ rows = list(csv.reader(open(sass_csv)))
 hdr, data = rows[1], rows[2:]
 assert len(data) == len(insts), (len(data), len(insts))
 
-# source line -> region
-src = open(src_path).read().splitlines()
-base = os.path.basename(src_path)
-region_of = {}
-name = "?"
-for i, l in enumerate(src, 1):
-    m = re.match(r"^(?:static\s+)?(?:__device__|__global__|template|struct|int |void )", l)
-    if m and "(" in l and not l.startswith("template"):
-        mm = re.search(r"([A-Za-z_0-9]+)\s*\(", l[l.find("__") if "__launch_bounds__" not in l else 0:])
-        ids = re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*\(", l)
-        ids = [x for x in ids if x not in ("__launch_bounds__", "__device__", "__global__")]
-        if ids:
-            name = ids[0]
-    elif l.startswith("struct ") and "{" in l:
-        name = l.split()[1]
-    mk = re.match(r"^\s+// ---- (.*?) -*$", l)
-    if mk and name.startswith("k_project"):
-        name = "k_project: " + mk.group(1)[:40]
-    region_of[i] = name
+# source line -> region, for the given source and every other file of its directory (headers with inlined code)
+def region_map(path):
+    out, name = {}, "?"
+    for i, l in enumerate(open(path).read().splitlines(), 1):
+        m = re.match(r"^(?:static\s+)?(?:__device__|__global__|template|struct|int |void )", l)
+        if m and "(" in l and not l.startswith("template"):
+            ids = re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*\(", l)
+            ids = [x for x in ids if x not in ("__launch_bounds__", "__device__", "__global__")]
+            if ids:
+                name = ids[0]
+        elif l.startswith("struct ") and "{" in l:
+            name = l.split()[1]
+        mk = re.match(r"^\s+// ---- (.*?) -*$", l)
+        if mk and (name.startswith("k_project") or name.startswith("query_tail")):
+            name = name.split(":")[0] + ": " + mk.group(1)[:40]
+        out[i] = name
+    return out
+
+src_dir = os.path.dirname(os.path.abspath(src_path))
+maps = {f: region_map(os.path.join(src_dir, f)) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))}
 
 def key(cur):
     if cur is None:
         return "?"
     f, ln, rest = cur
-    if f == base:
-        return region_of.get(ln, "?")
+    if f in maps:
+        return maps[f].get(ln, "?")
     for ff, l2 in re.findall(r'inlined at "([^"]+)", line (\d+)', rest):
-        if os.path.basename(ff) == base:
-            return region_of.get(int(l2), "?") + " (lib)"
+        if os.path.basename(ff) in maps:
+            return maps[os.path.basename(ff)].get(int(l2), "?") + " (lib)"
     return f
 
 ie, smp = hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -85,3 +86,20 @@ print(f"{'region':44s} {'inst%':>6s} {'inst/q':>7s} {'smpl%':>6s} {'static':>6s}
 for n, v in reg.most_common(34):
     st = ", ".join(f"{a[6:]}:{100 * b / ts:.1f}" for a, b in regstall[n].most_common(3))
     print(f"{n[:44]:44s} {100 * v / ti:6.2f} {v / nq:7.1f} {100 * regs[n] / ts:6.2f} {stat[n]:6d} {hot[n]:5d}  {st}")
+
+# per source line detail of the regions named in PLO_REGION_LINES (comma-separated substrings)
+want = [w for w in os.environ.get("PLO_REGION_LINES", "").split(",") if w]
+if want:
+    per_line = collections.Counter()
+    ops = collections.defaultdict(collections.Counter)
+    for (op, cur), d in zip(insts, data):
+        k = key(cur)
+        if any(w in k for w in want) and cur is not None:
+            per_line[(cur[0], cur[1], k)] += int(d[ie])
+            ops[(cur[0], cur[1], k)][op.split()[0] if not op.startswith("@") else op.split()[1]] += int(d[ie])
+    for (f, ln, k), v in per_line.most_common(45):
+        text = ""
+        pth = os.path.join(src_dir, f)
+        if os.path.exists(pth):
+            text = open(pth).read().splitlines()[ln - 1].strip()[:90]
+        print(f"{v / nq:7.1f}  {f}:{ln:<5d} {text}   [{', '.join(f'{a}:{b / nq:.1f}' for a, b in ops[(f, ln, k)].most_common(4))}]")

@@ -27,7 +27,8 @@ kp = []
 for i in range(3):
     ctx.set_target(target); ctx.set_source(source); T, rs = ctx.register(); kp.append(ctx.last_kernel_timings()["ms_project_mean"]); each = ctx.last_project_times()
 ctx.set_profiling(False)
+misses = ctx.last_tile_misses()
 steady = ctx.time_project_kernel(T, 10)
 fp = float(np.abs(T).sum())
 print(f"[{tag}] iters {rs['iters']} pairs {rs['pairs']} fp {fp:.12f} | register ms median {np.median(regs):.4f} min {np.min(regs):.4f} | "
-      f"k_project mean/launch {np.mean(kp):.4f} | steady (converged pose) {steady:.4f} | per launch {np.round(each, 3).tolist()}", flush=True)
+      f"k_project mean/launch {np.mean(kp):.4f} | steady (converged pose) {steady:.4f} | per launch {np.round(each, 3).tolist()} | tile misses {misses.tolist()}", flush=True)
