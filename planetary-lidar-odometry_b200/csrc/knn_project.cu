@@ -120,15 +120,13 @@ struct ProjectOut {
 };
 
 // device-side counters of one projection (settled + cold launch); all zero between projections
-// (CNT_STORE_MODE is rewritten by k_project_settled at the start of every projection)
-enum { CNT_CHUNK = 0, CNT_BLOCKS_DONE = 1, CNT_N_MISS = 2, CNT_MISS_CURSOR = 3, CNT_SETTLED_GROUP = 4, CNT_MISS_MODE = 5, CNT_RESET_END = 6,
-       CNT_STORE_MODE = 6, CNT_N = 8 };
+enum { CNT_CHUNK = 0, CNT_BLOCKS_DONE = 1, CNT_N_MISS = 2, CNT_MISS_CURSOR = 3, CNT_SETTLED_GROUP = 4, CNT_GROUPS_DONE = 5, CNT_N = 8 };
 
-constexpr int kGroup = 32;   // queries a warp of k_project_settled takes at a time
+constexpr int kGroup = 32;   // queries a warp takes at a time on the settled path
 
 struct LoopSync {
   int* counters;    // [CNT_N]
-  int* miss_list;   // [M] queries k_project_settled hands to k_project_cold
+  int* miss_list;   // [M] queries the settled path hands to the tree walk; -1 = empty slot
 };
 
 // ---- the per-query tail shared by both kernels: 1-NN gates, per-neighbour filters, IMLS sum, output --------
@@ -253,7 +251,7 @@ __device__ __forceinline__ void transform_query(const double* __restrict__ T, co
   }
 }
 
-// ---- k_project_cold ---------------------------------------------------------------------------------------
+// ---- the tree walk of one query (cold path) -----------------------------------------------------------------
 
 // carry reference: the previous query of the warp's chunk
 struct Carry {
@@ -261,10 +259,10 @@ struct Carry {
   int pos;   // lane j < k: position of the previous query's j-th neighbour (valid while kf is finite)
 };
 
-template <bool PCA, int LEVELS, bool HOOKS, bool STORE>
+template <bool PCA, int LEVELS, bool HOOKS>
 __device__ __forceinline__ void cold_query(const MapView& m, const float4* __restrict__ sp, const float4* __restrict__ sn,
                                            const DevParams& P, const ProjectOut& out, const double* __restrict__ T, int qi,
-                                           int use_prev, int n_tgt, float inflate, WarpScratch& ws, Carry& cy, int lane) {
+                                           int use_prev, int n_tgt, bool store, float inflate, WarpScratch& ws, Carry& cy, int lane) {
   const float4 p = __ldg(&sp[qi]);
   const float4 nf = __ldg(&sn[qi]);
   float xf, yf, zf, nxf, nyf, nzf;
@@ -306,10 +304,11 @@ __device__ __forceinline__ void cold_query(const MapView& m, const float4* __res
   TileSink sink;
   sink.pts = out.tile_pts + (size_t)qi * kTileSlots;
   sink.meta = out.tile_meta + qi;
-  if (n_tgt > 0) knn_topk<LEVELS, STORE>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane, &sink, ref_kf, inflate);   // :372-375 ALLOW_SELF_MATCH
+  sink.store = store;
+  if (n_tgt > 0) knn_topk<LEVELS, true>(m, xf, yf, zf, Df0, refine, P.r2, P.k, true, ws, tk, ss, lane, &sink, ref_kf, inflate);   // :372-375 ALLOW_SELF_MATCH
   else {
     tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1; ss.n_leaf = ss.n_node = ss.n_cand = 0;
-    if (STORE && lane == 0) *sink.meta = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (store && lane == 0) *sink.meta = make_float4(0.f, 0.f, 0.f, -1.f);
   }
   float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane < P.k && tk.d2 < CUDART_INF) pp = __ldg(&m.pts[tk.pos]);
@@ -319,108 +318,16 @@ __device__ __forceinline__ void cold_query(const MapView& m, const float4* __res
   cy.pos = tk.pos;
 }
 
-// STORE: the instantiation that leaves candidate tiles behind.  Both instantiations are launched for every projection
-// and the one that does not match the loop state (`warm`: the last pose step was small) returns at once: the walk
-// of the first projections keeps the lean instruction footprint it needs (32 KB instruction cache).
-template <bool PCA, int LEVELS, bool HOOKS, bool STORE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project_cold(const __grid_constant__ MapView m,
-                                                                               const float4* __restrict__ sp,
-                                                                               const float4* __restrict__ sn,
-                                                                               const DevCounts* __restrict__ counts,
-                                                                               DevState* __restrict__ st,
-                                                                               const __grid_constant__ DevParams P,
-                                                                               const __grid_constant__ ProjectOut out,
-                                                                               const __grid_constant__ LoopSync L, int chunk_arg) {
-  // which instantiation runs was fixed by k_project_settled at the start of this projection: the loop state itself
-  // changes when the other instantiation's last block runs the solve
-  if (st->done || (L.counters[CNT_STORE_MODE] != 0) != STORE) return;
-  __shared__ WarpScratch s_ws[kWarpsPerBlock];
-  // lane and the warp's scratch offset are made opaque: left to itself the compiler rematerialises them from the
-  // special registers ~40 times per query (S2R + shifts: 6 % of the kernel's instructions)
-  int lane = threadIdx.x & 31;
-  unsigned ws_ofs = (threadIdx.x >> 5) * (unsigned)sizeof(WarpScratch);
-  asm volatile("" : "+r"(lane), "+r"(ws_ofs));
-  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(reinterpret_cast<char*>(s_ws) + ws_ofs);
-  const int use_prev = st->use_prev;
-  const int warm = STORE ? 1 : 0;     // the pose is settling: short chunks, block-local ranges, tiles left behind
-  const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
-  const int n_src = counts->n_source;
-  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
-  const int miss_mode = L.counters[CNT_MISS_MODE];   // k_project_settled ran ahead of this launch: only its misses are left
-  const int n_miss = miss_mode ? L.counters[CNT_N_MISS] : 0;
-  const float inflate = miss_mode ? PLO_TILE_INFLATE : PLO_TILE_INFLATE_ALL;
-  // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
-  __shared__ double T[12];
-  __shared__ int s_next;
-  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
-  if (threadIdx.x == 0) s_next = 0;
-  __syncthreads();
+// ---- a query answered from its candidate tile (settled path) -----------------------------------------------
 
-  // Each warp walks chunks of `chunk` consecutive source points (handed out dynamically, one
-  // atomic per chunk: per-query cost varies a lot).  Correctness never depends on the order of
-  // the source points, only the quality of the carry bound does.
-  // Locality: once the pose is settling the first PLO_BLOCK_RANGES % of the source is cut into one contiguous range
-  // per block, whose warps take chunks from a shared-memory counter -- the warps of a block then work on neighbouring
-  // scan points and share leaves and boxes in L1; the rest is handed out through the global counter and evens out
-  // the tail.  With the long chunks and the uneven cost of the first projections the ranges unbalance the blocks
-  // (measured: second projection 0.41 -> 0.49 ms).
-  // After k_project_settled only its misses are left: one query per fetch (no carry between unrelated queries).
-  const int n_static = (!miss_mode && warm && PLO_BLOCK_RANGES > 0) ? (int)((long long)n_src * PLO_BLOCK_RANGES / 100) / chunk * chunk : 0;
-  const int per_block = ((n_static + (int)gridDim.x - 1) / (int)gridDim.x + chunk - 1) / chunk * chunk;
-  const int b0 = min((int)blockIdx.x * per_block, n_static), b1 = min(b0 + per_block, n_static);
-  bool own_range = n_static > 0;
-  while (true) {
-    int c0 = 0, c1 = 0;
-    if (miss_mode) {
-      if (lane == 0) c0 = atomicAdd(&L.counters[CNT_MISS_CURSOR], 1);
-      c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
-      if (c0 >= n_miss) break;
-      c0 = __ldcg(&L.miss_list[c0]);
-      c1 = c0 + 1;
-    } else {
-      int c_end = n_src;
-      if (own_range) {
-        if (lane == 0) c0 = b0 + atomicAdd(&s_next, 1) * chunk;
-        c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
-        c_end = b1;
-        if (c0 >= b1) own_range = false;
-      }
-      if (!own_range) {
-        if (lane == 0) c0 = n_static + atomicAdd(&L.counters[CNT_CHUNK], 1) * chunk;
-        c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
-        c_end = n_src;
-      }
-      if (c0 >= n_src) break;
-      c1 = min(c0 + chunk, c_end);
-    }
-    Carry cy;
-    cy.kf = CUDART_INF_F; cy.x = cy.y = cy.z = 0.f; cy.pos = -1;
-    for (int qi = c0; qi < c1; ++qi) cold_query<PCA, LEVELS, HOOKS, STORE>(m, sp, sn, P, out, T, qi, use_prev, n_tgt, inflate, ws, cy, lane);
-  }
-
-  // ---- epilogue: the last block to get here resets the projection's counters ----
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  __threadfence();
-  if (atomicAdd(&L.counters[CNT_BLOCKS_DONE], 1) != (int)gridDim.x - 1) return;
-  __threadfence();
-  const int it = st->iters;
-  if (it < 32) st->miss_hist[it] = miss_mode ? n_miss : -1;
-  if (STORE) st->tiles_ready = 1;   // every query handled by this kernel since the reset left a tile (or an invalid mark) behind
-  for (int i = 0; i < CNT_RESET_END; ++i) L.counters[i] = 0;
-}
-
-// ---- k_project_settled ------------------------------------------------------------------------------------
-
-constexpr int kSettledWarps = 16;
-
-struct TileScratch {
+struct __align__(16) TileScratch {
   double d2[kTileSlots];    // exact distances of the candidates that passed the bound (+inf: not acceptable)
   float4 xyz[kTileSlots];   // their coordinates, w = bits of the position in the sorted arrays
   int idx[kTileSlots];      // stripped-cloud indices (fetched only when two distances tie, or for the hooks)
   double od2[PLO_MAX_K];    // rank r -> distance
   int oslot[PLO_MAX_K];     // rank r -> candidate slot
 };
+static_assert(sizeof(TileScratch) <= sizeof(WarpScratch), "the two per-warp scratch layouts share one shared-memory slice");
 
 // ranks of the C candidates under the (d2, index) order; ranks < k are scattered: ts.od2[r] / ts.oslot[r]
 __device__ __forceinline__ void rank_tile(const MapView& m, TileScratch& ts, int C, int k, int lane) {
@@ -456,106 +363,210 @@ __device__ __forceinline__ void rank_tile(const MapView& m, TileScratch& ts, int
   __syncwarp();
 }
 
+// One query whose tile covers its bound bD: the tile (two coalesced 512-byte loads, evict-first: the tiles stream
+// through, the map stays in L2) filtered by the same lower-bound test as a leaf, exact fp64 distances, ranks, tail.
+// Returns false when the query needs the tree after all (query_tail).
 template <bool PCA, bool HOOKS>
-__global__ void __launch_bounds__(kSettledWarps * 32, 2) k_project_settled(const __grid_constant__ MapView m,
-                                                                           const float4* __restrict__ sp,
-                                                                           const float4* __restrict__ sn,
-                                                                           const DevCounts* __restrict__ counts,
-                                                                           const DevState* __restrict__ st,
-                                                                           const __grid_constant__ DevParams P,
-                                                                           const __grid_constant__ ProjectOut out,
-                                                                           const __grid_constant__ LoopSync L) {
-  // first kernel of every projection: fixes which k_project_cold instantiation follows (see there)
-  if (blockIdx.x == 0 && threadIdx.x == 0) L.counters[CNT_STORE_MODE] = st->warm;
-  if (st->done || !st->use_prev || !st->tiles_ready) return;
-  __shared__ TileScratch s_ts[kSettledWarps];
-  __shared__ double T[12];
-  const int lane = threadIdx.x & 31;
-  TileScratch& ts = s_ts[threadIdx.x >> 5];
-  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
-  if (blockIdx.x == 0 && threadIdx.x == 0) L.counters[CNT_MISS_MODE] = 1;   // tells k_project_cold (next in the stream) to work off the miss list
-  __syncthreads();
-  const int n_src = counts->n_source;
-  const int G = (n_src + kGroup - 1) / kGroup;
+__device__ __forceinline__ bool tile_query(const MapView& m, const DevParams& P, const ProjectOut& out, int qj, float bx, float by,
+                                           float bz, float bnx, float bny, float bnz, float bD, TileScratch& ts, int lane) {
   const unsigned lt = (1u << lane) - 1u;
-  const float r2f = bound_f(P.r2);
-  while (true) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(&L.counters[CNT_SETTLED_GROUP], 1);
-    g = __shfl_sync(PLO_FULL_MASK, g, 0);
-    if (g >= G) break;
-    // ---- lane = query: transform, temporal bound, tile validity ----
-    const int qi = g * kGroup + lane;
-    const bool act = qi < n_src;
-    float xf = 0.f, yf = 0.f, zf = 0.f, nxf = 0.f, nyf = 0.f, nzf = 0.f, Df = CUDART_INF_F;
-    bool valid = false;
-    if (act) {
-      transform_query(T, __ldg(&sp[qi]), __ldg(&sn[qi]), P.transform_normal, xf, yf, zf, nxf, nyf, nzf);
-      const float kprev = out.kd2f[qi];
-      const float4 meta = out.tile_meta[qi];
-      if (kprev < CUDART_INF_F && meta.w > 0.f) {
-        const float4 xp = out.qx[qi];
-        Df = fminf(tri_bound(kprev, xf, yf, zf, xp.x, xp.y, xp.z), r2f);
-        // sqrt(D) + |x - x_ref| <= sqrt(e2), rounded against the claim (NaN compares false)
-        valid = __fadd_ru(__fsqrt_ru(Df), dist_hi(xf, yf, zf, meta.x, meta.y, meta.z)) <= __fsqrt_rd(meta.w);
+  const float4* tp = out.tile_pts + (size_t)qj * kTileSlots;
+  const float4 c0 = __ldcs(tp + lane), c1 = __ldcs(tp + 32 + lane);
+  const bool pass0 = __float_as_int(c0.w) >= 0 && dist_lo2(bx, by, bz, c0) <= bD;
+  const bool pass1 = __float_as_int(c1.w) >= 0 && dist_lo2(bx, by, bz, c1) <= bD;
+  const unsigned b0 = __ballot_sync(PLO_FULL_MASK, pass0), b1 = __ballot_sync(PLO_FULL_MASK, pass1);
+  const int C = __popc(b0) + __popc(b1);
+  const double dqx = (double)bx, dqy = (double)by, dqz = (double)bz;
+  if (pass0) {   // exact fp64 distance, libnabo's acceptance rule (:372-375: ALLOW_SELF_MATCH)
+    const int o = __popc(b0 & lt);
+    const double d2 = dist2_exact(dqx, dqy, dqz, c0);
+    ts.d2[o] = (d2 <= P.r2) ? d2 : CUDART_INF;
+    ts.xyz[o] = c0;
+  }
+  if (pass1) {
+    const int o = __popc(b0) + __popc(b1 & lt);
+    const double d2 = dist2_exact(dqx, dqy, dqz, c1);
+    ts.d2[o] = (d2 <= P.r2) ? d2 : CUDART_INF;
+    ts.xyz[o] = c1;
+  }
+  __syncwarp();
+  rank_tile(m, ts, C, P.k, lane);
+  TopK tk;
+  tk.d2 = ts.od2[lane];
+  const int slot = ts.oslot[lane];
+  float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
+  tk.pos = -1;
+  tk.idx = -1;
+  if (lane < P.k && tk.d2 < CUDART_INF) {
+    pp = ts.xyz[slot];
+    tk.pos = __float_as_int(pp.w);
+    tk.idx = HOOKS ? __float_as_int(__ldg(&m.pts[tk.pos]).w) : 0;   // only its sign matters without the hooks
+  }
+  __syncwarp();
+  SearchStats ss;
+  ss.on = HOOKS;
+  ss.n_leaf = 0; ss.n_node = 0; ss.n_cand = C + 50000;
+  float kd2f_now;
+  return query_tail<PCA, 1, HOOKS, true>(m, P, out, qj, bx, by, bz, bnx, bny, bnz, tk, pp, nullptr, ss, lane, kd2f_now);
+}
+
+// ---- k_project ----------------------------------------------------------------------------------------------
+//
+// ONE launch per projection, persistent grid (2 blocks of 16 warps per SM).
+// * Without tiles (first projections of a registration): every warp walks chunks of consecutive source points
+//   through the tree.
+// * With tiles (left behind by a projection made while the pose was settling): a warp takes GROUPS of 32 consecutive
+//   queries -- lane = query for the per-query scalars (transform, temporal bound, tile validity), then warp = query
+//   for each valid one (tile_query).  Queries whose tile does not cover the bound are appended to a miss list; warps
+//   that run out of groups work that list off with the tree walk WHILE the other warps still stream tiles (an entry
+//   is its own ready flag: -1 until written, reset by its consumer), so the latency-bound walks of the few misses
+//   hide behind the streaming of the many hits.
+// Every per-query result is bitwise the same whichever path produced it.
+template <bool PCA, int LEVELS, bool HOOKS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const __grid_constant__ MapView m,
+                                                                          const float4* __restrict__ sp,
+                                                                          const float4* __restrict__ sn,
+                                                                          const DevCounts* __restrict__ counts,
+                                                                          DevState* __restrict__ st,
+                                                                          const __grid_constant__ DevParams P,
+                                                                          const __grid_constant__ ProjectOut out,
+                                                                          const __grid_constant__ LoopSync L, int chunk_arg) {
+  if (st->done) return;
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
+  // lane and the warp's scratch offset are made opaque: left to itself the compiler rematerialises them from the
+  // special registers ~40 times per query (S2R + shifts: 6 % of the kernel's instructions)
+  int lane = threadIdx.x & 31;
+  unsigned ws_ofs = (threadIdx.x >> 5) * (unsigned)sizeof(WarpScratch);
+  asm volatile("" : "+r"(lane), "+r"(ws_ofs));
+  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(reinterpret_cast<char*>(s_ws) + ws_ofs);
+  const int use_prev = st->use_prev;
+  const bool store = st->warm != 0;   // the pose is settling: short chunks, block-local ranges, tiles left behind
+  const bool tiles = use_prev && st->tiles_ready;
+  const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
+  const int n_src = counts->n_source;
+  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
+  // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
+  __shared__ double T[12];
+  __shared__ int s_next;
+  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
+  if (threadIdx.x == 0) s_next = 0;
+  __syncthreads();
+
+  if (tiles) {
+    TileScratch& ts = reinterpret_cast<TileScratch&>(ws);
+    const int G = (n_src + kGroup - 1) / kGroup;
+    const unsigned lt = (1u << lane) - 1u;
+    const float r2f = bound_f(P.r2);
+    // ---- groups of 32 queries from their tiles ----
+    while (true) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(&L.counters[CNT_SETTLED_GROUP], 1);
+      g = __shfl_sync(PLO_FULL_MASK, g, 0);
+      if (g >= G) break;
+      // lane = query: transform, temporal bound, tile validity
+      const int qi = g * kGroup + lane;
+      const bool act = qi < n_src;
+      float xf = 0.f, yf = 0.f, zf = 0.f, nxf = 0.f, nyf = 0.f, nzf = 0.f, Df = CUDART_INF_F;
+      bool valid = false;
+      if (act) {
+        transform_query(T, __ldg(&sp[qi]), __ldg(&sn[qi]), P.transform_normal, xf, yf, zf, nxf, nyf, nzf);
+        const float kprev = out.kd2f[qi];
+        const float4 meta = out.tile_meta[qi];
+        if (kprev < CUDART_INF_F && meta.w > 0.f) {
+          const float4 xp = out.qx[qi];
+          Df = fminf(tri_bound(kprev, xf, yf, zf, xp.x, xp.y, xp.z), r2f);
+          // sqrt(D) + |x - x_ref| <= sqrt(e2), rounded against the claim (NaN compares false)
+          valid = __fadd_ru(__fsqrt_ru(Df), dist_hi(xf, yf, zf, meta.x, meta.y, meta.z)) <= __fsqrt_rd(meta.w);
+        }
       }
-    }
-    const unsigned hit = __ballot_sync(PLO_FULL_MASK, valid);
-    const unsigned miss = __ballot_sync(PLO_FULL_MASK, act && !valid);
-    if (miss) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&L.counters[CNT_N_MISS], __popc(miss));
-      base = __shfl_sync(PLO_FULL_MASK, base, 0);
-      if (act && !valid) L.miss_list[base + __popc(miss & lt)] = qi;
-    }
-    // ---- warp = query, for every query of the group whose tile covers its bound ----
-    for (unsigned rem = hit; rem; rem &= rem - 1u) {
-      const int j = __ffs(rem) - 1;
-      const int qj = g * kGroup + j;
-      const float bx = __shfl_sync(PLO_FULL_MASK, xf, j), by = __shfl_sync(PLO_FULL_MASK, yf, j), bz = __shfl_sync(PLO_FULL_MASK, zf, j);
-      const float bnx = __shfl_sync(PLO_FULL_MASK, nxf, j), bny = __shfl_sync(PLO_FULL_MASK, nyf, j), bnz = __shfl_sync(PLO_FULL_MASK, nzf, j);
-      const float bD = __shfl_sync(PLO_FULL_MASK, Df, j);
-      const float4* tp = out.tile_pts + (size_t)qj * kTileSlots;
-      const float4 c0 = __ldcs(tp + lane), c1 = __ldcs(tp + 32 + lane);
-      const bool pass0 = __float_as_int(c0.w) >= 0 && dist_lo2(bx, by, bz, c0) <= bD;
-      const bool pass1 = __float_as_int(c1.w) >= 0 && dist_lo2(bx, by, bz, c1) <= bD;
-      const unsigned b0 = __ballot_sync(PLO_FULL_MASK, pass0), b1 = __ballot_sync(PLO_FULL_MASK, pass1);
-      const int C = __popc(b0) + __popc(b1);
-      const double dqx = (double)bx, dqy = (double)by, dqz = (double)bz;
-      if (pass0) {   // exact fp64 distance, libnabo's acceptance rule (:372-375: ALLOW_SELF_MATCH)
-        const int o = __popc(b0 & lt);
-        const double d2 = dist2_exact(dqx, dqy, dqz, c0);
-        ts.d2[o] = (d2 <= P.r2) ? d2 : CUDART_INF;
-        ts.xyz[o] = c0;
+      const unsigned hit = __ballot_sync(PLO_FULL_MASK, valid);
+      const unsigned miss = __ballot_sync(PLO_FULL_MASK, act && !valid);
+      if (miss) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&L.counters[CNT_N_MISS], __popc(miss));
+        base = __shfl_sync(PLO_FULL_MASK, base, 0);
+        if (act && !valid) __stcg(&L.miss_list[base + __popc(miss & lt)], qi);
       }
-      if (pass1) {
-        const int o = __popc(b0) + __popc(b1 & lt);
-        const double d2 = dist2_exact(dqx, dqy, dqz, c1);
-        ts.d2[o] = (d2 <= P.r2) ? d2 : CUDART_INF;
-        ts.xyz[o] = c1;
+      // warp = query, for every query of the group whose tile covers its bound
+      for (unsigned rem = hit; rem; rem &= rem - 1u) {
+        const int j = __ffs(rem) - 1;
+        const int qj = g * kGroup + j;
+        const float bx = __shfl_sync(PLO_FULL_MASK, xf, j), by = __shfl_sync(PLO_FULL_MASK, yf, j), bz = __shfl_sync(PLO_FULL_MASK, zf, j);
+        const float bnx = __shfl_sync(PLO_FULL_MASK, nxf, j), bny = __shfl_sync(PLO_FULL_MASK, nyf, j), bnz = __shfl_sync(PLO_FULL_MASK, nzf, j);
+        const float bD = __shfl_sync(PLO_FULL_MASK, Df, j);
+        const bool ok = tile_query<PCA, HOOKS>(m, P, out, qj, bx, by, bz, bnx, bny, bnz, bD, ts, lane);
+        if (!ok && lane == 0) __stcg(&L.miss_list[atomicAdd(&L.counters[CNT_N_MISS], 1)], qj);   // needs the tree after all
       }
       __syncwarp();
-      rank_tile(m, ts, C, P.k, lane);
-      TopK tk;
-      tk.d2 = ts.od2[lane];
-      const int slot = ts.oslot[lane];
-      float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-      tk.pos = -1;
-      tk.idx = -1;
-      if (lane < P.k && tk.d2 < CUDART_INF) {
-        pp = ts.xyz[slot];
-        tk.pos = __float_as_int(pp.w);
-        tk.idx = HOOKS ? __float_as_int(__ldg(&m.pts[tk.pos]).w) : 0;   // only its sign matters without the hooks
-      }
-      __syncwarp();
-      SearchStats ss;
-      ss.on = HOOKS;
-      ss.n_leaf = 0; ss.n_node = 0; ss.n_cand = C + 50000;
-      float kd2f_now;
-      const bool ok = query_tail<PCA, 1, HOOKS, true>(m, P, out, qj, bx, by, bz, bnx, bny, bnz, tk, pp, nullptr, ss, lane, kd2f_now);
-      if (!ok && lane == 0) L.miss_list[atomicAdd(&L.counters[CNT_N_MISS], 1)] = qj;   // needs the tree after all
+      if (lane == 0) atomicAdd(&L.counters[CNT_GROUPS_DONE], 1);   // after this group's last append
     }
   }
+  // ---- tree walk: every query in chunks (no tiles), or the settled path's misses as they come in ----
+  // Each warp walks chunks of `chunk` consecutive source points (handed out dynamically, one
+  // atomic per chunk: per-query cost varies a lot).  Correctness never depends on the order of
+  // the source points, only the quality of the carry bound does.
+  // Locality: once the pose is settling the first PLO_BLOCK_RANGES % of the source is cut into one contiguous range
+  // per block, whose warps take chunks from a shared-memory counter -- the warps of a block then work on neighbouring
+  // scan points and share leaves and boxes in L1; the rest is handed out through the global counter and evens out
+  // the tail.  With the long chunks and the uneven cost of the first projections the ranges unbalance the blocks
+  // (measured: second projection 0.41 -> 0.49 ms).
+  {
+    const float inflate = tiles ? PLO_TILE_INFLATE : PLO_TILE_INFLATE_ALL;
+    const int G = (n_src + kGroup - 1) / kGroup;
+    const int n_static = (!tiles && store && PLO_BLOCK_RANGES > 0) ? (int)((long long)n_src * PLO_BLOCK_RANGES / 100) / chunk * chunk : 0;
+    const int per_block = ((n_static + (int)gridDim.x - 1) / (int)gridDim.x + chunk - 1) / chunk * chunk;
+    const int b0 = min((int)blockIdx.x * per_block, n_static), b1 = min(b0 + per_block, n_static);
+    bool own_range = n_static > 0;
+    while (true) {
+      int c0 = 0, c1 = 0;
+      if (tiles) {
+        if (lane == 0) {
+          const int i = atomicAdd(&L.counters[CNT_MISS_CURSOR], 1);
+          volatile int* vl = L.miss_list;
+          volatile int* vc = L.counters;
+          while (true) {
+            if (i >= n_src) { c0 = -2; break; }                  // the list cannot grow this long: nothing left for this warp
+            c0 = vl[i];
+            if (c0 >= 0) { vl[i] = -1; break; }                 // consumed: the slot is free for the next projection
+            if (vc[CNT_GROUPS_DONE] >= G && i >= vc[CNT_N_MISS]) { c0 = -2; break; }   // every group is through and the list is shorter
+            __nanosleep(200);
+          }
+        }
+        c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+        if (c0 < 0) break;
+        c1 = c0 + 1;
+      } else {
+        int c_end = n_src;
+        if (own_range) {
+          if (lane == 0) c0 = b0 + atomicAdd(&s_next, 1) * chunk;
+          c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+          c_end = b1;
+          if (c0 >= b1) own_range = false;
+        }
+        if (!own_range) {
+          if (lane == 0) c0 = n_static + atomicAdd(&L.counters[CNT_CHUNK], 1) * chunk;
+          c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
+          c_end = n_src;
+        }
+        if (c0 >= n_src) break;
+        c1 = min(c0 + chunk, c_end);
+      }
+      Carry cy;
+      cy.kf = CUDART_INF_F; cy.x = cy.y = cy.z = 0.f; cy.pos = -1;
+      for (int qi = c0; qi < c1; ++qi) cold_query<PCA, LEVELS, HOOKS>(m, sp, sn, P, out, T, qi, use_prev, n_tgt, store, inflate, ws, cy, lane);
+    }
+  }
+
+  // ---- epilogue: the last block to get here resets the projection's counters ----
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  if (atomicAdd(&L.counters[CNT_BLOCKS_DONE], 1) != (int)gridDim.x - 1) return;
+  __threadfence();
+  const int it = st->iters;
+  if (it < 32) st->miss_hist[it] = tiles ? ((volatile int*)L.counters)[CNT_N_MISS] : -1;
+  if (store) st->tiles_ready = 1;   // every query handled by the tree walk since the reset left a tile (or an invalid mark) behind
+  for (int i = 0; i < CNT_N; ++i) L.counters[i] = 0;
 }
 
 // ---- PCA normals: IMLSICPMatcher::ComputeNormal (src/imls_icp.cpp:753-794) -------------
@@ -656,7 +667,11 @@ int plo_reserve_query_buffers(plo_ctx* c, bool hooks) {
   PLO_CUDA(c, c->q_tile_pts.reserve(sizeof(float4) * kTileSlots * m));
   PLO_CUDA(c, c->q_tile_meta.reserve(sizeof(float4) * m));
   PLO_TRY(reserve_zeroed(c, c->sync_counters, sizeof(int) * CNT_N));
-  PLO_CUDA(c, c->miss_list.reserve(sizeof(int) * m));
+  {
+    const void* before = c->miss_list.p;
+    PLO_CUDA(c, c->miss_list.reserve(sizeof(int) * m));
+    if (c->miss_list.p != before) PLO_CUDA(c, cudaMemsetAsync(c->miss_list.p, 0xff, c->miss_list.cap, c->stream));   // -1 = empty slot
+  }
   if (hooks) {
     PLO_CUDA(c, c->q_height.reserve(sizeof(double) * m));
     PLO_CUDA(c, c->q_nn1_idx.reserve(sizeof(int) * m));
@@ -696,34 +711,25 @@ struct ProjectLaunch {
   DevState* st;
   ProjectOut out;
   LoopSync sync;
-  int blocks_cold, blocks_settled, chunk;
+  int blocks, chunk;
 };
 
-template <bool PCA, bool HOOKS, bool STORE>
-void launch_cold_levels(plo_ctx* c, const ProjectLaunch& a) {
+template <bool PCA, bool HOOKS>
+void launch_project_levels(plo_ctx* c, const ProjectLaunch& a) {
   const int T = kWarpsPerBlock * 32;
   switch (c->n_levels) {   // an empty map (n_levels == 0) never walks the tree: any instantiation does
     case 0:
-    case 1: k_project_cold<PCA, 1, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 2: k_project_cold<PCA, 2, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 3: k_project_cold<PCA, 3, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 4: k_project_cold<PCA, 4, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 5: k_project_cold<PCA, 5, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    default: k_project_cold<PCA, 6, HOOKS, STORE><<<a.blocks_cold, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 1: k_project<PCA, 1, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 2: k_project<PCA, 2, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 3: k_project<PCA, 3, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 4: k_project<PCA, 4, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 5: k_project<PCA, 5, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    default: k_project<PCA, 6, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
   }
-}
-
-template <bool PCA, bool HOOKS>
-void launch_both(plo_ctx* c, const ProjectLaunch& a) {
-  k_project_settled<PCA, HOOKS><<<a.blocks_settled, kSettledWarps * 32, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync);
-  launch_cold_levels<PCA, HOOKS, false>(c, a);
-  launch_cold_levels<PCA, HOOKS, true>(c, a);
 }
 }  // namespace
 
-// One projection = k_project_settled (returns at once unless the previous projections left tiles behind) followed by
-// the two instantiations of k_project_cold (everything, or the settled kernel's misses), of which the one matching
-// the loop state runs.
+// One projection = one k_project launch.
 int plo_launch_project(plo_ctx* c, bool hooks) {
   if (c->m_raw == 0) return PLO_OK;
   ProjectLaunch a;
@@ -750,18 +756,16 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   a.chunk = (c->m_raw < 16 * slots) ? 1 : 0;
   if (c->tune_chunk >= 0) a.chunk = c->tune_chunk;   // tuning knob (0 = device-side policy)
   const int64_t warps = std::max<int64_t>(c->m_raw, 1);
-  a.blocks_cold = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
-  const int64_t groups = (warps + kGroup - 1) / kGroup;
-  a.blocks_settled = (int)std::max<int64_t>(1, std::min<int64_t>((groups + kSettledWarps - 1) / kSettledWarps, (int64_t)plo_grid(c, 2)));
+  a.blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
   if (c->dprm.use_pca_normals) {
-    if (hooks) launch_both<true, true>(c, a);
-    else launch_both<true, false>(c, a);
+    if (hooks) launch_project_levels<true, true>(c, a);
+    else launch_project_levels<true, false>(c, a);
   } else {
-    if (hooks) launch_both<false, true>(c, a);
-    else launch_both<false, false>(c, a);
+    if (hooks) launch_project_levels<false, true>(c, a);
+    else launch_project_levels<false, false>(c, a);
   }
   c->prev_valid = true;   // later projections of the same clouds may use this one's k-th distances
-  c->launches += 3;
+  c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
 }

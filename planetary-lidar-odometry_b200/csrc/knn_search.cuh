@@ -45,7 +45,7 @@ struct SearchStats {
   __device__ __forceinline__ void node() { if (on) n_node++; }
 };
 
-struct WarpScratch {
+struct __align__(16) WarpScratch {   // (16: the settled path overlays its own layout, with float4 members, on the same slice)
   double d2[kCap];   // phase C: exact distances
   int idx[kCap];     // phase C: stripped-cloud indices
   int pos[kCap];     // phase B: positions of the buffered candidates
@@ -411,40 +411,50 @@ constexpr int kTileSlots = 64;
 struct TileSink {
   float4* pts;    // [kTileSlots] this query's slots: x, y, z, w = bits of the position (-1 = empty)
   float4* meta;   // x_ref.xyz, w = e2 (<= 0: no valid tile)
+  bool store;     // the pose is settling: leave a tile behind (and look a little farther than needed to give it a margin)
 };
 
 // after a walk the buffer holds every point with lo <= Df.  Keep at most kTileSlots of them (threshold t <= Df
-// lowered until they fit): every point outside then has d2 >= lo > t.
-__device__ __forceinline__ void store_tile(const MapView& m, const TileSink& sink, WarpScratch& ws, const Collector& col, float qx,
-                                           float qy, float qz, int lane) {
+// lowered until they fit): every point outside then has d2 >= lo > t.  Then the buffer goes back to the proven
+// bound `tight` for phase C; returns its new count.  Out of line: only the projections made while the pose is
+// settling come here, the walk of the first projections keeps its instruction footprint.
+__device__ __noinline__ int store_tile(const MapView& m, const TileSink* sink, WarpScratch* wsp, int count, float Df, int shrinks,
+                                       float tight, float qx, float qy, float qz) {
+  WarpScratch& ws = *wsp;
+  const int lane = threadIdx.x & 31;
   __syncwarp();
-  float t = col.Df;
-  int cnt = col.count;
+  float t = Df;
+  int cnt = count;
   for (int pass = 0; cnt > kTileSlots && pass < 32; ++pass) {   // 0.85^32 < 0.006: beyond that (ties at zero distance) no tile
     t = __fmul_rd(t, 0.85f);
     cnt = 0;
-    for (int base = 0; base < col.count; base += 32) {
+    for (int base = 0; base < count; base += 32) {
       const int i = base + lane;
-      cnt += __popc(__ballot_sync(PLO_FULL_MASK, i < col.count && ws.lo[i] <= t));
+      cnt += __popc(__ballot_sync(PLO_FULL_MASK, i < count && ws.lo[i] <= t));
     }
   }
   const bool fits = cnt <= kTileSlots;
   int o = 0;
-  for (int base = 0; base < col.count; base += 32) {
+  for (int base = 0; base < count; base += 32) {
     const int i = base + lane;
-    const bool keep = fits && i < col.count && ws.lo[i] <= t;
+    const bool keep = fits && i < count && ws.lo[i] <= t;
     const unsigned b = __ballot_sync(PLO_FULL_MASK, keep);
     if (keep) {
       const int ps = ws.pos[i];
       const float4 p = __ldg(&m.pts[ps]);
-      __stcs(&sink.pts[o + __popc(b & ((1u << lane) - 1u))], make_float4(p.x, p.y, p.z, __int_as_float(ps)));
+      __stcs(&sink->pts[o + __popc(b & ((1u << lane) - 1u))], make_float4(p.x, p.y, p.z, __int_as_float(ps)));
     }
     o += __popc(b);
   }
-  for (int i = o + lane; i < kTileSlots; i += 32) __stcs(&sink.pts[i], make_float4(0.f, 0.f, 0.f, __int_as_float(-1)));
+  for (int i = o + lane; i < kTileSlots; i += 32) __stcs(&sink->pts[i], make_float4(0.f, 0.f, 0.f, __int_as_float(-1)));
   // a bound that met the massive-tie fallback (exact_shrink) no longer describes the buffer: no tile
-  const bool valid = fits && col.shrinks < 1000 && t > 0.f && t < CUDART_INF_F;
-  if (lane == 0) *sink.meta = make_float4(qx, qy, qz, valid ? t : -1.f);
+  const bool valid = fits && shrinks < 1000 && t > 0.f && t < CUDART_INF_F;
+  if (lane == 0) *sink->meta = make_float4(qx, qy, qz, valid ? t : -1.f);
+  if (tight < Df) {
+    __syncwarp();
+    count = filter_buffer(ws, count, tight, lane);
+  }
+  return count;
 }
 
 // exact k-NN of q (float32 coordinates, as the reference stores the transformed point).
@@ -460,7 +470,7 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
   tk.idx = -1;
   tk.pos = -1;
   if (!(isfinite(qx) && isfinite(qy) && isfinite(qz))) {
-    if constexpr (TILE) { if (lane == 0) *sink->meta = make_float4(0.f, 0.f, 0.f, -1.f); }
+    if constexpr (TILE) { if (sink->store && lane == 0) *sink->meta = make_float4(0.f, 0.f, 0.f, -1.f); }
     return;
   }
   const float r2f_lo = __double2float_rd(r2);   // "certainly within the radius" threshold
@@ -477,19 +487,19 @@ __device__ __forceinline__ void knn_topk(const MapView& m, float qx, float qy, f
     Collect<LEVELS, true>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
   } else {
     if constexpr (TILE) {
-      // a wider ball than the proven bound asks for, so that the tile outlives the next small moves of the query
-      // (`inflate` x the reference's k-th distance, unless the proven bound is already looser)
-      tight = col.Df;
-      col.Df = fminf(fmaxf(tight, __fmul_ru(ref_kf, inflate)), bound_f(r2));
+      if (sink->store) {
+        // a wider ball than the proven bound asks for, so that the tile outlives the next small moves of the query
+        // (`inflate` x the reference's k-th distance, unless the proven bound is already looser)
+        tight = col.Df;
+        col.Df = fminf(fmaxf(tight, __fmul_ru(ref_kf, inflate)), bound_f(r2));
+      }
     }
     Collect<LEVELS, false>::run(m, 0, qx, qy, qz, r2f_lo, r2, allow_self, k, ws, col, st, lane);
   }
   if constexpr (TILE) {
-    store_tile(m, *sink, ws, col, qx, qy, qz, lane);
-    if (tight < col.Df) {   // back to the proven bound for phase C
-      __syncwarp();
-      col.count = filter_buffer(ws, col.count, tight, lane);
-      col.Df = tight;
+    if (sink->store) {
+      col.count = store_tile(m, sink, &ws, col.count, col.Df, col.shrinks, tight, qx, qy, qz);
+      col.Df = fminf(col.Df, tight);
     }
   }
   __syncwarp();
