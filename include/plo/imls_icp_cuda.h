@@ -7,6 +7,9 @@
  *   SolveMotionEstimationProblemWeightedLS_CUDA
  *                                       <->  SolveMotionEstimationProblemWeightedLS
  *                                            (include/solver.h:92-98, src/solver.cpp:168-220)
+ *   SolveMotionEstimationProblem{LS,RANSAC,DRPM}_CUDA
+ *                                       <->  SolveMotionEstimationProblem{LS,RANSAC,DRPM}
+ *                                            (include/solver.h:84-90, :100-114, :129-139)
  *
  * Header-only, C++11, no dependency beyond the C ABI: it is templated on the point / vector /
  * matrix types so that it compiles here without PCL / Eigen and, in the reference tree, with
@@ -105,12 +108,15 @@ class IMLSICPMatcherCUDA {
   /* solve_method.method / solve_method.RANSAC.* of config.json (src/laser_odometry.cpp:606 -> :173-275,
    * :196-244): picks the solver the resident loop (Match) and solveMotionEstimationProblem() below use.
    * Accepted: "WeightedLS_CUDA" / "Weighted LS", "LS" / "LS_CUDA" (trimmed, src/solver.cpp:74-166),
-   * "RANSAC" with final_solve_method "Weighted LS" or "DRPM" (src/solver.cpp:222-385, :499-603).
+   * "RANSAC" with final_solve_method "LS", "Weighted LS" or "DRPM" (src/solver.cpp:222-385, :366-384, :499-603).
+   * ls_threshold = solve_method.LS.threshold (:190); ransac_ls_threshold = solve_method.RANSAC.LS_threshold, the trim
+   * fraction of the final "LS" inside RANSAC (:205) -- a key of its own in config.json; < 0: same as ls_threshold.
    * Anything else throws (the reference prints "Invalid SOLVE_METHOD!", :271). */
   void setSolveMethod(const std::string& solve_method, double ls_threshold = 0.02, double ransac_distance_threshold = 0.8,
                       double huber_threshold = 0.648, const std::string& final_solve_method = "DRPM",
                       int ransac_max_iterations = 5000, double ransac_min_inliers_percentage = 0.95,
-                      double drpm_threshold = 0.05, double drpm_stdev_points = 0.02, double drpm_stdev_normals = 0.05) {
+                      double drpm_threshold = 0.05, double drpm_stdev_points = 0.02, double drpm_stdev_normals = 0.05,
+                      double ransac_ls_threshold = -1.0) {
     if (solve_method == "WeightedLS_CUDA" || solve_method == "Weighted LS") {
       params_.solver = PLO_SOLVER_WLS;
     } else if (solve_method == "LS" || solve_method == "LS_CUDA") {
@@ -118,7 +124,10 @@ class IMLSICPMatcherCUDA {
       params_.ls_threshold = ls_threshold;
     } else if (solve_method == "RANSAC") {
       params_.solver = PLO_SOLVER_RANSAC;
-      if (final_solve_method == "LS") { params_.ransac_final = PLO_FINAL_LS; params_.ls_threshold = ls_threshold; }
+      if (final_solve_method == "LS") {
+        params_.ransac_final = PLO_FINAL_LS;
+        params_.ls_threshold = ransac_ls_threshold >= 0.0 ? ransac_ls_threshold : ls_threshold;
+      }
       else if (final_solve_method == "Weighted LS") params_.ransac_final = PLO_FINAL_WLS;
       else if (final_solve_method == "DRPM") params_.ransac_final = PLO_FINAL_DRPM;
       else throw std::runtime_error("plo: unknown RANSAC final_solve_method \"" + final_solve_method + "\"");
@@ -148,6 +157,30 @@ class IMLSICPMatcherCUDA {
     return true;
   }
   const double* lastDrpmProbabilities() const { return last_probs_; }
+
+  /* bool ImplicitMLSFunction(PointType& x, double& height), include/imls_icp.h:75-76, src/imls_icp.cpp:301-483:
+   * x = the (already transformed) point with its normal; false = fewer than 3 usable neighbours (:463-466). */
+  bool ImplicitMLSFunction(PointT& x, double& height) {
+    const float* f = reinterpret_cast<const float*>(&x);
+    const float in[6] = {f[0], f[1], f[2], f[4], f[5], f[6]};
+    int32_t ok = 0;
+    check(ctx_, plo_imls_height(ctx_, in, 1, &height, &ok), "ImplicitMLSFunction");
+    return ok != 0;
+  }
+
+  /* Eigen::Vector3d ComputeNormal(std::vector<Eigen::Vector3d>& nearPoints), include/imls_icp.h:84,
+   * src/imls_icp.cpp:753-794. */
+  template <typename Vec3T>
+  Vec3T ComputeNormal(std::vector<Vec3T>& nearPoints) {
+    std::vector<double> p(3 * nearPoints.size());
+    for (size_t i = 0; i < nearPoints.size(); ++i)
+      for (int k = 0; k < 3; ++k) p[3 * i + k] = nearPoints[i][k];
+    double n[3];
+    check(ctx_, plo_compute_normal(ctx_, p.data(), (int64_t)nearPoints.size(), n), "ComputeNormal");
+    Vec3T out;
+    for (int k = 0; k < 3; ++k) out[k] = n[k];
+    return out;
+  }
 
   /* include/imls_icp.h:79-82, src/imls_icp.cpp:496-745 (+ the transform of
    * src/laser_odometry.cpp:527-549).  in_cloud <- surviving transformed source points,
@@ -243,6 +276,97 @@ bool SolveMotionEstimationProblemWeightedLS_CUDA(plo_ctx* ctx, const std::vector
         "SolveMotionEstimationProblemWeightedLS_CUDA");
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) deltaTrans(r, c) = D[r * 4 + c];
+  return true;
+}
+
+namespace detail {
+template <typename Vec3T>
+inline void flatten3(const std::vector<Vec3T>& a, const std::vector<Vec3T>& b, const std::vector<Vec3T>& c, std::vector<double>& s,
+                     std::vector<double>& d, std::vector<double>& n) {
+  const size_t m = a.size();
+  s.resize(3 * m); d.resize(3 * m); n.resize(3 * m);
+  for (size_t i = 0; i < m; ++i)
+    for (int k = 0; k < 3; ++k) { s[3 * i + k] = a[i][k]; d[3 * i + k] = b[i][k]; n[3 * i + k] = c[i][k]; }
+}
+template <typename Mat4T>
+inline void unflatten16(const double D[16], Mat4T& M) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) M(r, c) = D[r * 4 + c];
+}
+inline void check_rc(plo_ctx* ctx, int rc, const char* what) {
+  if (rc != PLO_OK) throw std::runtime_error(std::string("plo: ") + what + ": " + plo_last_error(ctx));
+}
+}  // namespace detail
+
+/* SolveMotionEstimationProblemLS, include/solver.h:84-90 — same argument list
+ * (source_cloud, ref_cloud, ref_normals, deltaTrans, timestamp, threshold). */
+template <typename Vec3T, typename Mat4T>
+bool SolveMotionEstimationProblemLS_CUDA(plo_ctx* ctx, const std::vector<Vec3T>& source_cloud, const std::vector<Vec3T>& ref_cloud,
+                                         const std::vector<Vec3T>& ref_normals, Mat4T& deltaTrans, const std::string& /*timestamp*/,
+                                         const double threshold) {
+  std::vector<double> s, d, n;
+  detail::flatten3(source_cloud, ref_cloud, ref_normals, s, d, n);
+  double D[16];
+  detail::check_rc(ctx, plo_solve_ls_host(ctx, s.data(), d.data(), n.data(), (int64_t)source_cloud.size(), threshold, D, nullptr),
+                   "SolveMotionEstimationProblemLS_CUDA");
+  detail::unflatten16(D, deltaTrans);
+  return true;
+}
+
+/* SolveMotionEstimationProblemRANSAC, include/solver.h:100-114 — same argument list (source_cloud, ref_cloud, ref_normals,
+ * deltaTrans, timestamp, max_iterations, distance_threshold, min_inliers_percentage, huber_threshold, final_solve_method,
+ * ls_threshold, drpm_threshold, drpm_stdev_points, drpm_stdev_normals) + the seed that replaces the reference's unseeded
+ * rand().  Returns false for an unknown final_solve_method, like the reference (src/solver.cpp:377-384). */
+template <typename Vec3T, typename Mat4T>
+bool SolveMotionEstimationProblemRANSAC_CUDA(plo_ctx* ctx, const std::vector<Vec3T>& source_cloud, const std::vector<Vec3T>& ref_cloud,
+                                             const std::vector<Vec3T>& ref_normals, Mat4T& deltaTrans, const std::string& /*timestamp*/,
+                                             const int max_iterations, const double distance_threshold,
+                                             const double min_inliers_percentage, const double huber_threshold,
+                                             const std::string final_solve_method, const double ls_threshold,
+                                             const double drpm_threshold, const double drpm_stdev_points,
+                                             const double drpm_stdev_normals, const unsigned long long seed = 1ull) {
+  plo_params p;
+  plo_default_params(&p);
+  if (final_solve_method == "LS") p.ransac_final = PLO_FINAL_LS;
+  else if (final_solve_method == "Weighted LS") p.ransac_final = PLO_FINAL_WLS;
+  else if (final_solve_method == "DRPM") p.ransac_final = PLO_FINAL_DRPM;
+  else return false;
+  p.ransac_max_iterations = max_iterations;
+  p.ransac_distance_threshold = distance_threshold;
+  p.ransac_min_inliers_percentage = min_inliers_percentage;
+  p.huber_threshold = huber_threshold;
+  p.ls_threshold = ls_threshold;
+  p.drpm_threshold = drpm_threshold;
+  p.drpm_stdev_points = drpm_stdev_points;
+  p.drpm_stdev_normals = drpm_stdev_normals;
+  p.ransac_seed = seed;
+  std::vector<double> s, d, n;
+  detail::flatten3(source_cloud, ref_cloud, ref_normals, s, d, n);
+  double D[16];
+  detail::check_rc(ctx, plo_solve_ransac_host(ctx, s.data(), d.data(), n.data(), (int64_t)source_cloud.size(), &p, D, nullptr, nullptr, nullptr),
+                   "SolveMotionEstimationProblemRANSAC_CUDA");
+  detail::unflatten16(D, deltaTrans);
+  return true;
+}
+
+/* SolveMotionEstimationProblemDRPM, include/solver.h:129-139 — same argument list (source_cloud, ref_cloud, ref_normals,
+ * deltaTrans, weights, timestamp, threshold, stdev_points, stdev_normals); `weights` may be empty (unit weights). */
+template <typename Vec3T, typename Mat4T, typename WeightsT>
+bool SolveMotionEstimationProblemDRPM_CUDA(plo_ctx* ctx, const std::vector<Vec3T>& source_cloud, const std::vector<Vec3T>& ref_cloud,
+                                           const std::vector<Vec3T>& ref_normals, Mat4T& deltaTrans, const WeightsT& weights,
+                                           const std::string& /*timestamp*/, const double threshold, const double stdev_points,
+                                           const double stdev_normals) {
+  std::vector<double> s, d, n, w;
+  detail::flatten3(source_cloud, ref_cloud, ref_normals, s, d, n);
+  if ((size_t)weights.size() == source_cloud.size() && !source_cloud.empty()) {
+    w.resize(source_cloud.size());
+    for (size_t i = 0; i < w.size(); ++i) w[i] = weights[i];
+  }
+  double D[16];
+  detail::check_rc(ctx, plo_solve_drpm_host(ctx, s.data(), d.data(), n.data(), w.empty() ? nullptr : w.data(),
+                                            (int64_t)source_cloud.size(), threshold, stdev_points, stdev_normals, D, nullptr),
+                   "SolveMotionEstimationProblemDRPM_CUDA");
+  detail::unflatten16(D, deltaTrans);
   return true;
 }
 

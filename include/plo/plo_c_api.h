@@ -196,6 +196,40 @@ PLO_API int plo_get_query_results(plo_ctx* ctx, int32_t* status, double* height)
  * is_get_normals == 0 */
 PLO_API int plo_get_target_normals(plo_ctx* ctx, double* out);
 
+/* bool IMLSICPMatcher::ImplicitMLSFunction(PointType& x, double& height) (include/imls_icp.h:75-76,
+ * src/imls_icp.cpp:301-483) for a batch: xyz_normal6 = n x {x, y, z, nx, ny, nz} float32 (the point as the matcher
+ * sees it, i.e. already transformed; its normal feeds the angle filter).  ok[i] = the function's return value
+ * (>= 3 usable neighbours); height[i] is NaN where ok[i] == 0.  No 1-NN gates: those belong to ProjSourcePtToSurface. */
+PLO_API int plo_imls_height(plo_ctx* ctx, const float* xyz_normal6, int64_t n, double* height, int32_t* ok);
+/* Eigen::Vector3d IMLSICPMatcher::ComputeNormal(std::vector<Eigen::Vector3d>&) (include/imls_icp.h:84,
+ * src/imls_icp.cpp:753-794): mean, population covariance, unit eigenvector of the smallest eigenvalue; like the
+ * reference, no sign disambiguation (the matcher's own PCA pass orients +z, deviation D2). */
+PLO_API int plo_compute_normal(plo_ctx* ctx, const double* pts3, int64_t n, double normal[3]);
+
+/* ---- the other reference-shaped solver entry points: host vectors in, 4x4 out ----------------------------
+ * src / ref / nrm are n x 3 doubles (std::vector<Eigen::Vector3d>::data()), delta is row-major.  The pairs are staged
+ * in the float32 arrays the device solvers work on, so every coordinate must be float32-representable -- what
+ * getXYZ / getNormals (include/common.h:51-75) produce at the reference's call site (src/laser_odometry.cpp:595-599);
+ * anything else is PLO_ERR_UNSUPPORTED (plo_solve_wls_host takes arbitrary doubles).  These calls use the context's
+ * per-query arrays: the last projection's pairs and temporal state are gone afterwards, the clouds stay.
+ *
+ * SolveMotionEstimationProblemLS (include/solver.h:84-90, src/solver.cpp:74-166): `threshold` = trim fraction. */
+PLO_API int plo_solve_ls_host(plo_ctx* ctx, const double* src, const double* ref, const double* nrm, int64_t n,
+                              double threshold, double delta[16], int32_t* rank);
+/* SolveMotionEstimationProblemRANSAC (include/solver.h:100-114, src/solver.cpp:222-385).  `ransac` carries the
+ * arguments of the reference's signature: ransac_max_iterations, ransac_distance_threshold,
+ * ransac_min_inliers_percentage, huber_threshold, ransac_final (final_solve_method), ls_threshold, drpm_threshold,
+ * drpm_stdev_points, drpm_stdev_normals, and ransac_seed (the reference's unseeded rand()); its other fields are
+ * ignored.  probs: the six DRPM non-degeneracy probabilities (zero unless final = DRPM). */
+PLO_API int plo_solve_ransac_host(plo_ctx* ctx, const double* src, const double* ref, const double* nrm, int64_t n,
+                                  const plo_params* ransac, double delta[16], double probs[6], int64_t* inliers,
+                                  int32_t* hypotheses);
+/* SolveMotionEstimationProblemDRPM (include/solver.h:129-139, src/solver.cpp:499-603, include/degeneracy.h:14-131):
+ * weights w (n doubles, NULL = unit) are used as they are. */
+PLO_API int plo_solve_drpm_host(plo_ctx* ctx, const double* src, const double* ref, const double* nrm, const double* w,
+                                int64_t n, double threshold, double stdev_points, double stdev_normals, double delta[16],
+                                double probs[6]);
+
 /* ---- solver -----------------------------------------------------------------------
  * plo_solve_wls == SolveMotionEstimationProblemWeightedLS (src/solver.cpp:168-220,
  * include/solver.h:92-98) on the device-resident pairs of the last plo_project with the

@@ -13,7 +13,10 @@ from ._lib import PloError, PloFrontendParams, PloParams, default_params, fronte
 from .context import Context  # noqa: F401
 from .matcher import IMLSICPMatcher  # noqa: F401
 from .odometry import LaserOdometry, save_poses_tum  # noqa: F401
-from .solver import SolveMotionEstimationProblemWeightedLS_CUDA, solveMotionEstimationProblem  # noqa: F401
+from . import solver  # noqa: F401
+from .solver import (SolveMotionEstimationProblemDRPM_CUDA, SolveMotionEstimationProblemLS_CUDA,  # noqa: F401
+                     SolveMotionEstimationProblemRANSAC_CUDA, SolveMotionEstimationProblemWeightedLS_CUDA,
+                     solveMotionEstimationProblem)
 
 __all__ = ["synth", "config", "Context", "IMLSICPMatcher", "LaserOdometry", "PloError", "PloParams",
            "default_params", "frontend_default_params", "PloFrontendParams", "SolveMotionEstimationProblemWeightedLS_CUDA", "solveMotionEstimationProblem",

@@ -13,8 +13,9 @@ Accepted selections
                            "weights": "huber_exp"), "LS" / "LS_CUDA" (the reference's trimmed LS,
                            src/solver.cpp:74-166, threshold from solve_method.LS.threshold), or
                            "RANSAC" (the config.json default chain, src/solver.cpp:222-385) with
-                           final_solve_method "Weighted LS" or "DRPM" (src/solver.cpp:499-603)
-Everything else the reference lists (plane_ICP, Ceres, ICP, Teaser, RANSAC->LS,
+                           final_solve_method "LS" (trim fraction RANSAC.LS_threshold, src/laser_odometry.cpp:205),
+                           "Weighted LS" or "DRPM" (src/solver.cpp:499-603)
+Everything else the reference lists (plane_ICP, Ceres, ICP, Teaser,
 tensor voting, projected distance) is outside the hot-path scope and raises.
 """
 from __future__ import annotations
@@ -49,7 +50,9 @@ DEFAULT_CONFIG = {
             "delta_dist_threshold": 0.001,
             "delta_angle_threshold": 0.0001745353,
             "LS": {"threshold": 0.02},
-            "RANSAC": {"distance_threshold": 0.8, "huber_threshold": 0.648, "final_solve_method": "Weighted LS"},
+            "RANSAC": {"max_iterations": 5000, "distance_threshold": 0.8, "min_inliers_percentage": 0.95, "huber_threshold": 0.648,
+                       "final_solve_method": "Weighted LS", "LS_threshold": 0.02, "DRPM_threshold": 0.05,
+                       "DRPM_stdev_points": 0.02, "DRPM_stdev_normals": 0.05},
         },
     },
 }
@@ -57,6 +60,10 @@ DEFAULT_CONFIG = {
 
 class ConfigError(ValueError):
     pass
+
+
+# final_solve_method strings of SolveMotionEstimationProblemRANSAC (src/solver.cpp:366-384)
+RANSAC_FINALS = {"LS": _lib.FINAL_LS, "Weighted LS": _lib.FINAL_WLS, "DRPM": _lib.FINAL_DRPM}
 
 
 def load_config(path: str | None = None) -> dict:
@@ -121,6 +128,7 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
     else:
         raise ConfigError(f"Invalid SOLVE_METHOD! ({smethod!r})")
     rs = _get(sm, "RANSAC", default={}, required=False) or {}
+    ls_cfg = _get(sm, "LS", default={}, required=False) or {}
     return _lib.default_params(
         iterations=int(_get(sm, "iterations")),
         h=float(_get(im, "h")), r=float(_get(im, "r")),
@@ -138,7 +146,9 @@ def params_from_config(cfg: dict) -> _lib.PloParams:
         ransac_distance_threshold=float(rs.get("distance_threshold", 0.8)),
         huber_threshold=float(rs.get("huber_threshold", 0.648)),
         solver=solver,
-        ls_threshold=float((_get(sm, "LS", default={}, required=False) or {}).get("threshold", 0.02)),
+        # the trim fraction of the final "LS" inside RANSAC is its own key (src/laser_odometry.cpp:205 -> src/solver.cpp:366-371)
+        ls_threshold=float(rs.get("LS_threshold", ls_cfg.get("threshold", 0.02)) if solver == _lib.SOLVER_RANSAC
+                           else ls_cfg.get("threshold", 0.02)),
         ransac_max_iterations=int(rs.get("max_iterations", 5000)),
         ransac_min_inliers_percentage=float(rs.get("min_inliers_percentage", 0.95)),
         ransac_final=ransac_final,

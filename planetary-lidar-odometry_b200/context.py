@@ -267,6 +267,50 @@ class Context:
         self._ck(self.L.plo_solve_wls_host(self.h, _ptr(src), _ptr(ref), _ptr(nrm), _ptr(w), src.shape[0], _ptr(d), C.byref(rank)))
         return d.reshape(4, 4), rank.value
 
+    def solve_ls_host(self, src, ref, nrm, threshold: float = 0.02):
+        """SolveMotionEstimationProblemLS on caller pairs (n x 3 doubles each, float32-representable)"""
+        src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
+        d = np.empty(16, np.float64)
+        rank = C.c_int32()
+        self._ck(self.L.plo_solve_ls_host(self.h, _ptr(src), _ptr(ref), _ptr(nrm), src.shape[0], float(threshold), _ptr(d), C.byref(rank)))
+        return d.reshape(4, 4), rank.value
+
+    def solve_ransac_host(self, src, ref, nrm, params: PloParams | None = None):
+        """SolveMotionEstimationProblemRANSAC on caller pairs; `params` carries the RANSAC / final-solver fields"""
+        src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
+        d = np.empty(16, np.float64)
+        pr = np.zeros(6, np.float64)
+        inl, hyp = C.c_int64(), C.c_int32()
+        p = params or self.params
+        self._ck(self.L.plo_solve_ransac_host(self.h, _ptr(src), _ptr(ref), _ptr(nrm), src.shape[0], C.byref(p), _ptr(d), _ptr(pr),
+                                              C.byref(inl), C.byref(hyp)))
+        return d.reshape(4, 4), dict(probs=pr, inliers=int(inl.value), hypotheses=int(hyp.value))
+
+    def solve_drpm_host(self, src, ref, nrm, w=None, threshold: float = 0.05, stdev_points: float = 0.02, stdev_normals: float = 0.05):
+        """SolveMotionEstimationProblemDRPM on caller pairs and weights"""
+        src, ref, nrm = (np.ascontiguousarray(a, np.float64) for a in (src, ref, nrm))
+        w = None if w is None else np.ascontiguousarray(w, np.float64)
+        d = np.empty(16, np.float64)
+        pr = np.zeros(6, np.float64)
+        self._ck(self.L.plo_solve_drpm_host(self.h, _ptr(src), _ptr(ref), _ptr(nrm), _ptr(w), src.shape[0], float(threshold),
+                                            float(stdev_points), float(stdev_normals), _ptr(d), _ptr(pr)))
+        return d.reshape(4, 4), pr
+
+    def imls_height(self, xyz_normal):
+        """ImplicitMLSFunction for a batch of (already transformed) points: (n, 6) float32 -> heights, ok flags"""
+        a = np.ascontiguousarray(xyz_normal, np.float32).reshape(-1, 6)
+        h = np.empty(a.shape[0], np.float64)
+        ok = np.empty(a.shape[0], np.int32)
+        self._ck(self.L.plo_imls_height(self.h, _ptr(a), a.shape[0], _ptr(h), _ptr(ok)))
+        return h, ok.astype(bool)
+
+    def compute_normal(self, pts) -> np.ndarray:
+        """ComputeNormal: unit eigenvector of the smallest eigenvalue of the points' population covariance"""
+        a = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        out = np.empty(3, np.float64)
+        self._ck(self.L.plo_compute_normal(self.h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
     def normal_equations(self):
         H = np.empty(21)
         g = np.empty(6)

@@ -645,6 +645,79 @@ __global__ void __launch_bounds__(kPcaWarps * 32) k_pca_normals(const __grid_con
   }
 }
 
+
+// ---- stand-alone matcher entry points of the reference's surface ------------------------------------------------
+
+// bool IMLSICPMatcher::ImplicitMLSFunction(PointType& x, double& height), src/imls_icp.cpp:301-483, for a batch of
+// points: k-NN within r (:372-375), per-neighbour filters (:380-460), cnt >= 3 (:463-466), the bandwidth quirk (:468)
+// and the IMLS sum (:470-480) -- without the 1-NN gates of ProjSourcePtToSurface.  One warp per point.
+template <bool PCA, int LEVELS>
+__global__ void __launch_bounds__(kPcaWarps * 32) k_imls_height(const __grid_constant__ MapView m, DevParams P,
+                                                                    const DevCounts* __restrict__ counts, const float* __restrict__ pts6,
+                                                                    int n, double* __restrict__ height, int* __restrict__ ok) {
+  __shared__ WarpScratch s_ws[kPcaWarps];
+  WarpScratch& ws = s_ws[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const float xf = pts6[6 * (size_t)i], yf = pts6[6 * (size_t)i + 1], zf = pts6[6 * (size_t)i + 2];
+    const double qx = (double)xf, qy = (double)yf, qz = (double)zf;
+    const double xnx = (double)pts6[6 * (size_t)i + 3], xny = (double)pts6[6 * (size_t)i + 4], xnz = (double)pts6[6 * (size_t)i + 5];
+    TopK tk;
+    tk.d2 = CUDART_INF; tk.idx = -1; tk.pos = -1;
+    SearchStats ss;
+    ss.on = false;
+    if (n_tgt > 0) knn_topk<LEVELS>(m, xf, yf, zf, CUDART_INF_F, true, P.r2, P.k, true, ws, tk, ss, lane);
+    const bool has = (lane < P.k) && (tk.d2 < CUDART_INF);
+    double pnx = 0.0, pny = 0.0, pnz = 0.0, ddx = 0.0, ddy = 0.0, ddz = 0.0;
+    bool keep = false;
+    if (has) {
+      const float4 pp = __ldg(&m.pts[tk.pos]);
+      if (PCA) { pnx = m.nrm_pca[3 * (size_t)tk.pos]; pny = m.nrm_pca[3 * (size_t)tk.pos + 1]; pnz = m.nrm_pca[3 * (size_t)tk.pos + 2]; }
+      else { const float4 nn = __ldg(&m.nrm[tk.pos]); pnx = (double)nn.x; pny = (double)nn.y; pnz = (double)nn.z; }
+      ddx = __dsub_rn(qx, (double)pp.x); ddy = __dsub_rn(qy, (double)pp.y); ddz = __dsub_rn(qz, (double)pp.z);
+      keep = finite3d(pnx, pny, pnz);
+      if (keep && P.angle_constraint) keep = !angle_exceeds(xnx, xny, xnz, pnx, pny, pnz, P);
+    }
+    const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, keep));
+    double h = CUDART_NAN;
+    if (cnt >= 3) {
+      const double cinv = -9.0 / __shfl_sync(PLO_FULL_MASK, tk.d2, cnt - 1);
+      double w = 0.0, pr = 0.0;
+      if (keep) {
+        w = exp(tk.d2 * cinv);
+        pr = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(w, ddx), pnx), __dmul_rn(__dmul_rn(w, ddy), pny)), __dmul_rn(__dmul_rn(w, ddz), pnz));
+      }
+      const double wsum = warp_sum(w), psum = warp_sum(pr);
+      h = psum / (wsum + 1e-5);
+    }
+    if (lane == 0) { height[i] = h; ok[i] = cnt >= 3 ? 1 : 0; }
+    __syncwarp();
+  }
+}
+
+// Eigen::Vector3d IMLSICPMatcher::ComputeNormal(std::vector<Eigen::Vector3d>&), src/imls_icp.cpp:753-794: mean,
+// population covariance, eigenvector of the smallest eigenvalue, normalised, no sign disambiguation.  One thread,
+// sums in the reference's order.
+__global__ void k_compute_normal(const double* __restrict__ p, int n, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mx = 0.0, my = 0.0, mz = 0.0;
+  for (int i = 0; i < n; ++i) { mx += p[3 * i]; my += p[3 * i + 1]; mz += p[3 * i + 2]; }   // :758-763
+  const double nd = (double)n;
+  mx /= nd; my /= nd; mz /= nd;
+  double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (int i = 0; i < n; ++i) {   // :766-771
+    const double dx = p[3 * i] - mx, dy = p[3 * i + 1] - my, dz = p[3 * i + 2] - mz;
+    c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
+  }
+  double v[3];
+  smallest_eigvec3(c00 / nd, c01 / nd, c02 / nd, c11 / nd, c12 / nd, c22 / nd, v);   // :776-778
+  const double nn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (nn > 0.0) { v[0] /= nn; v[1] /= nn; v[2] /= nn; }   // :791
+  out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+}
+
 }  // namespace
 
 namespace {
@@ -765,6 +838,35 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
     else launch_project_levels<false, false>(c, a);
   }
   c->prev_valid = true;   // later projections of the same clouds may use this one's k-th distances
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  return PLO_OK;
+}
+
+int plo_launch_imls_height(plo_ctx* c, const float* d_pts6, int n, double* d_height, int* d_ok) {
+  if (n <= 0) return PLO_OK;
+  const int grid = std::max(1, std::min((n + kPcaWarps - 1) / kPcaWarps, plo_grid(c, 4)));
+  const MapView mv = c->map_view();
+  const DevCounts* dc = c->counts.as<DevCounts>();
+#define PLO_IMLS_CASE(L)                                                                                                       \
+  case L:                                                                                                                      \
+    if (c->dprm.use_pca_normals) k_imls_height<true, L><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, dc, d_pts6, n, d_height, d_ok); \
+    else k_imls_height<false, L><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, dc, d_pts6, n, d_height, d_ok);                     \
+    break;
+  switch (std::max(c->n_levels, 1)) {
+    PLO_IMLS_CASE(1) PLO_IMLS_CASE(2) PLO_IMLS_CASE(3) PLO_IMLS_CASE(4) PLO_IMLS_CASE(5)
+    default:
+      if (c->dprm.use_pca_normals) k_imls_height<true, 6><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, dc, d_pts6, n, d_height, d_ok);
+      else k_imls_height<false, 6><<<grid, kPcaWarps * 32, 0, c->stream>>>(mv, c->dprm, dc, d_pts6, n, d_height, d_ok);
+  }
+#undef PLO_IMLS_CASE
+  c->launches++;
+  PLO_CUDA(c, cudaGetLastError());
+  return PLO_OK;
+}
+
+int plo_launch_compute_normal(plo_ctx* c, const double* d_pts3, int n, double* d_out) {
+  k_compute_normal<<<1, 32, 0, c->stream>>>(d_pts3, n, d_out);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;

@@ -214,7 +214,7 @@ __device__ __noinline__ void solve_from_sums(const double* s_sum, DevState* __re
   }
   double H[21], g[6];
   // weights are normalised to sum 1 in the reference (src/solver.cpp:361-364); same argmin
-  const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
+  const double scale = (!P.ext_weights && P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
   bool finite = true;
   for (int i = 0; i < 21; ++i) { H[i] = s_sum[i] * scale; finite = finite && isfinite(H[i]); }
   for (int i = 0; i < 6; ++i) { g[i] = s_sum[21 + i] * scale; finite = finite && isfinite(g[i]); }

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
                                                                  const DevCounts* __restrict__ counts,
                                                                  const DevState* __restrict__ st, DevParams P,
                                                                  double* __restrict__ partials, int respect_done,
-                                                                 const int* __restrict__ mask, int inliers_unit) {
+                                                                 const int* __restrict__ mask, int inliers_unit,
+                                                                 const double* __restrict__ w_ext) {
   if (respect_done && st->done) return;
   double acc[PLO_NSUM];
 #pragma unroll
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
     acc[29] += 1.0;
     if (mask != nullptr && mask[i] == 0) continue;   // trimmed LS, second pass: pair outside the kept rank window
     double w = 1.0;
-    if (P.weight_mode == PLO_W_HUBER_EXP) {
+    if (P.ext_weights) {
+      if (w_ext != nullptr) w = w_ext[i];   // caller-supplied weights (host-vector solver entry points), used as they are
+    } else if (P.weight_mode == PLO_W_HUBER_EXP) {
       w = huber_exp_weight(Tw, s, d, n, P);
       if (w < 0.0) continue;
       if (inliers_unit) w = 1.0;   // RANSAC -> "LS": the inlier subset, unweighted (src/solver.cpp:366-371)
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(32) k_drpm_eigen(DevState* __restrict__ st, De
   const int lane = threadIdx.x;
   {
     const double sw = st->sw;
-    const double scale = (P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;   // as k_solve_update
+    const double scale = (!P.ext_weights && P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;   // as k_solve_update
     if (lane == 0) {
       int t = 0;
       for (int a = 0; a < 6; ++a)
@@ -497,7 +500,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_drpm_noise(const float4* __r
                                                                const float4* __restrict__ qn,
                                                                const DevCounts* __restrict__ counts,
                                                                const DevState* __restrict__ st, DevParams P,
-                                                               double* __restrict__ partials2, int respect_done) {
+                                                               double* __restrict__ partials2, int respect_done,
+                                                               const double* __restrict__ w_ext) {
   if (respect_done && st->done) return;
   __shared__ double s_U[36];
   __shared__ double s_T[16];
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_drpm_noise(const float4* __r
   if (threadIdx.x < 36) s_U[threadIdx.x] = st->U[threadIdx.x];
   if (threadIdx.x < 16) s_T[threadIdx.x] = st->Tbest[threadIdx.x];
   __syncthreads();
-  const double inv_sw = st->sw > 0.0 ? 1.0 / st->sw : 0.0;
+  const double inv_sw = P.ext_weights ? 1.0 : (st->sw > 0.0 ? 1.0 / st->sw : 0.0);
   double acc[kNoiseSums];
 #pragma unroll
   for (int t = 0; t < kNoiseSums; ++t) acc[t] = 0.0;
@@ -518,9 +522,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_drpm_noise(const float4* __r
     const double p[3] = {(double)x.x, (double)x.y, (double)x.z};
     const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
     const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
-    double w = huber_exp_weight(s_T, p, d, n, P);
+    double w = P.ext_weights ? (w_ext != nullptr ? w_ext[i] : 1.0) : huber_exp_weight(s_T, p, d, n, P);
     if (w < 0.0) continue;
-    w *= inv_sw;   // weights normalised to sum 1 (src/solver.cpp:361-364)
+    w *= inv_sw;   // weights normalised to sum 1 (src/solver.cpp:361-364); caller-supplied ones are used as they are
     // B = [[-nx, px*nx], [0, nx]] (6x6), Ncov = diag(sp2 I3, sn2 I3)   (:39-51)
     const double nx[9] = {0, -n[2], n[1], n[2], 0, -n[0], -n[1], n[0], 0};
     const double px[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(64) k_drpm_finish(const double* __restrict__ p
   __syncthreads();
   if (threadIdx.x != 0) return;
   const double sw = st->sw;
-  const double scale = sw > 0.0 ? 1.0 / sw : 1.0;
+  const double scale = P.ext_weights ? 1.0 : (sw > 0.0 ? 1.0 / sw : 1.0);
   double H[21], g[6], Hf[36];
   for (int i = 0; i < 21; ++i) H[i] = st->H[i] * scale;
   for (int i = 0; i < 6; ++i) g[i] = st->g[i] * scale;
@@ -827,7 +831,7 @@ int plo_reserve_solver_buffers(plo_ctx* c) {
     PLO_CUDA(c, c->ls_tot.reserve(sizeof(int) * plo_sort_total_ints(kLsPasses)));
     PLO_CUDA(c, c->ls_mask.reserve(sizeof(int) * m));
   }
-  if (c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0) {
+  if ((c->dprm.solver == PLO_SOLVER_RANSAC || c->host_drpm_only) && c->m_raw > 0) {
     const size_t m = (size_t)c->m_raw;
     PLO_CUDA(c, c->h_src.reserve(sizeof(double) * 3 * m));   // also sized for plo_solve_wls_host
     PLO_CUDA(c, c->h_ref.reserve(sizeof(double) * 3 * m));
@@ -846,12 +850,15 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   const int adv = advance_loop ? 1 : 0;
   const cudaGraphConditionalHandle cond = (cudaGraphConditionalHandle)cond_handle;
   const int use_cond = cond_handle ? 1 : 0;
-  const bool ransac = c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0;
+  const bool drpm_only = c->host_drpm_only;   // plo_solve_drpm_host: the DRPM tail alone, on caller-supplied weights
+  const bool ransac = c->dprm.solver == PLO_SOLVER_RANSAC && c->m_raw > 0 && !drpm_only;
   const bool ransac_ls = ransac && c->dprm.ransac_final == PLO_FINAL_LS;   // trimmed LS on the inliers (src/solver.cpp:366-371)
   const bool trimmed = (c->dprm.solver == PLO_SOLVER_LS && c->m_raw > 0) || ransac_ls;
   const int in_unit = ransac_ls ? 1 : 0;
   DevParams P = c->dprm;
   if (trimmed) P.weight_mode = PLO_W_UNIT;       // SolveMotionEstimationProblemLS is unweighted
+  if (drpm_only) { P.ext_weights = 1; P.solver = PLO_SOLVER_WLS; }
+  const double* w_ext = c->host_w;
   if (ransac) P.weight_mode = PLO_W_HUBER_EXP;   // Huber/exp weights at the best hypothesis (src/solver.cpp:334-364);
                                                  // with final "LS" only their inlier test is used (in_unit)
   if (c->dprm.solver == PLO_SOLVER_RANSAC && !ransac) P.solver = PLO_SOLVER_WLS;   // empty source: nothing to sample
@@ -876,11 +883,11 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   if (c->m_raw > 0) {
     k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                         c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
-                                                        c->partials.as<double>(), adv, nullptr, in_unit);
+                                                        c->partials.as<double>(), adv, nullptr, in_unit, w_ext);
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
   }
-  const bool drpm = ransac && c->dprm.ransac_final == PLO_FINAL_DRPM;
+  const bool drpm = (ransac && c->dprm.ransac_final == PLO_FINAL_DRPM) || drpm_only;
   k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), c->m_raw > 0 ? g : 0, c->state.as<DevState>(), P, adv, cond,
                                             use_cond, trimmed ? 1 : (drpm ? 3 : 0));
   c->launches++;
@@ -891,7 +898,7 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
     PLO_CUDA(c, cudaGetLastError());
     k_drpm_noise<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                       c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
-                                                      c->partials2.as<double>(), adv);
+                                                      c->partials2.as<double>(), adv, w_ext);
     c->launches++;
     PLO_CUDA(c, cudaGetLastError());
     k_drpm_finish<<<1, 64, 0, c->stream>>>(c->partials2.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond);
@@ -919,7 +926,7 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   PLO_CUDA(c, cudaGetLastError());
   k_reduce_pairs<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                       c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
-                                                      c->partials.as<double>(), adv, c->ls_mask.as<int>(), 0);
+                                                      c->partials.as<double>(), adv, c->ls_mask.as<int>(), 0, nullptr);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   k_solve_update<<<1, 256, 0, c->stream>>>(c->partials.as<double>(), g, c->state.as<DevState>(), P, adv, cond, use_cond, 2);

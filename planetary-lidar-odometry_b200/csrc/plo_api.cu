@@ -90,6 +90,8 @@ static void flatten_params(plo_ctx* c) {
   d.drpm_sp2 = p.drpm_stdev_points * p.drpm_stdev_points;     // include/degeneracy.h:49
   d.drpm_sn2 = p.drpm_stdev_normals * p.drpm_stdev_normals;   // src/solver.cpp:486-497
   d.ransac_seed = p.ransac_seed ? p.ransac_seed : 1ull;
+  d.ext_weights = 0;
+  d.pad_ext = 0;
 }
 
 extern "C" {
@@ -183,7 +185,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket, &c->h_wext, &c->counts_saved,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
@@ -584,6 +586,40 @@ __global__ void k_export_normals(const float4* __restrict__ nrm, const double* _
 
 extern "C" {
 
+int plo_imls_height(plo_ctx* c, const float* xyz_normal6, int64_t n, double* height, int32_t* ok) {
+  if (!c || n < 0 || (n > 0 && (!xyz_normal6 || !height || !ok))) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_imls_height: bad argument");
+  if (!c->have_target) return plo_fail(c, PLO_ERR_STATE, "plo_imls_height: no target cloud set");
+  if (n == 0) return PLO_OK;
+  if (n > (int64_t)1 << 28) return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_imls_height: too many points");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  if (c->dprm.use_pca_normals) PLO_TRY(plo_launch_pca_normals(c));
+  const size_t in_b = sizeof(float) * 6 * (size_t)n, h_b = sizeof(double) * (size_t)n, ok_b = sizeof(int) * (size_t)n;
+  PLO_CUDA(c, c->scratch.reserve(in_b + h_b + ok_b + 64));
+  char* base = c->scratch.as<char>();
+  double* d_h = reinterpret_cast<double*>(base);
+  float* d_in = reinterpret_cast<float*>(base + h_b);
+  int* d_ok = reinterpret_cast<int*>(base + h_b + in_b);
+  PLO_CUDA(c, cudaMemcpyAsync(d_in, xyz_normal6, in_b, cudaMemcpyHostToDevice, c->stream));
+  PLO_TRY(plo_launch_imls_height(c, d_in, (int)n, d_h, d_ok));
+  PLO_CUDA(c, cudaMemcpyAsync(height, d_h, h_b, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaMemcpyAsync(ok, d_ok, ok_b, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
+int plo_compute_normal(plo_ctx* c, const double* pts3, int64_t n, double normal[3]) {
+  if (!c || !normal || n < 0 || (n > 0 && !pts3)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_compute_normal: bad argument");
+  if (n > 1 << 20) return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_compute_normal: more than 2^20 points");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, c->scratch.reserve(sizeof(double) * (3 * (size_t)std::max<int64_t>(n, 1) + 4)));
+  double* d_p = c->scratch.as<double>() + 4;
+  if (n > 0) PLO_CUDA(c, cudaMemcpyAsync(d_p, pts3, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  PLO_TRY(plo_launch_compute_normal(c, d_p, (int)n, c->scratch.as<double>()));
+  PLO_CUDA(c, cudaMemcpyAsync(normal, c->scratch.p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+  PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PLO_OK;
+}
+
 int plo_get_target_normals(plo_ctx* c, double* out) {
   if (!c || !out) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_get_target_normals: NULL argument");
   if (!c->have_target) return plo_fail(c, PLO_ERR_STATE, "plo_get_target_normals: no target cloud set");
@@ -653,6 +689,133 @@ int plo_solve_wls_host(plo_ctx* c, const double* src, const double* ref, const d
   PLO_TRY(fetch_state(c));
   memcpy(delta, c->h_state->delta, sizeof(double) * 16);
   if (rank) *rank = c->h_state->rank;
+  return PLO_OK;
+}
+
+// ---- reference-shaped LS / RANSAC / DRPM: host vectors in, 4x4 out (include/solver.h:84-90, :100-114, :129-139) ----
+//
+// The device solvers work on the float32 pairs a projection leaves behind (what getXYZ / getNormals promote to
+// double, include/common.h:51-75).  The host entry points stage caller pairs in the same arrays, so the coordinates
+// must be float32-representable -- which the reference's own call site guarantees (src/laser_odometry.cpp:595-599).
+namespace {
+struct HostPairs {
+  std::vector<float4> x, y, n;
+  std::vector<int> status;
+};
+
+int stage_host_pairs(plo_ctx* c, const char* who, const double* src, const double* ref, const double* nrm, int64_t n, HostPairs& hp) {
+  if (n < 0 || (n > 0 && (!src || !ref || !nrm))) return plo_fail(c, PLO_ERR_INVALID_ARG, std::string(who) + ": bad argument");
+  if (n > (int64_t)1 << 30) return plo_fail(c, PLO_ERR_UNSUPPORTED, std::string(who) + ": more than 2^30 pairs");
+  hp.x.resize((size_t)n); hp.y.resize((size_t)n); hp.n.resize((size_t)n); hp.status.assign((size_t)n, PLO_PT_OK);
+  bool exact = true;
+  auto f = [&exact](double v) { const float q = (float)v; exact = exact && ((double)q == v || v != v); return q; };
+  for (int64_t i = 0; i < n; ++i) {
+    float4 a = {f(src[3 * i]), f(src[3 * i + 1]), f(src[3 * i + 2]), 0.f};   // w = bits of PLO_PT_OK
+    hp.x[(size_t)i] = a;
+    hp.y[(size_t)i] = float4{f(ref[3 * i]), f(ref[3 * i + 1]), f(ref[3 * i + 2]), 0.f};
+    hp.n[(size_t)i] = float4{f(nrm[3 * i]), f(nrm[3 * i + 1]), f(nrm[3 * i + 2]), 0.f};
+  }
+  if (!exact)
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, std::string(who) + ": coordinates must be float32-representable (the pairs of getXYZ / "
+                    "getNormals, include/common.h:51-75); use plo_solve_wls_host for arbitrary doubles");
+  return PLO_OK;
+}
+
+// runs `solver` on caller pairs through the projection's own arrays; the context's clouds stay, its last projection
+// (pairs, temporal bounds, tiles) is gone afterwards
+int solve_host_pairs(plo_ctx* c, const char* who, const double* src, const double* ref, const double* nrm, const double* w,
+                     int64_t n, const plo_params& prm, bool drpm_only, double delta[16]) {
+  if (!c || !delta) return plo_fail(c, PLO_ERR_INVALID_ARG, std::string(who) + ": NULL argument");
+  HostPairs hp;
+  PLO_TRY(stage_host_pairs(c, who, src, ref, nrm, n, hp));
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  const plo_params saved_prm = c->prm;
+  const DevParams saved_dprm = c->dprm;
+  const int64_t saved_m = c->m_raw;
+  c->prm = prm;
+  flatten_params(c);
+  c->m_raw = n;
+  int rc = plo_reserve_query_buffers(c, false);
+  if (rc == PLO_OK) rc = plo_reserve_solver_buffers(c);
+  cudaError_t e = cudaSuccess;
+  if (rc == PLO_OK) {
+    e = c->counts_saved.reserve(sizeof(DevCounts));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->counts_saved.p, c->counts.p, sizeof(DevCounts), cudaMemcpyDeviceToDevice, c->stream);
+    const int n32 = (int)n;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&c->counts.as<DevCounts>()->n_source, &n32, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n > 0) {
+      e = cudaMemcpyAsync(c->q_x.p, hp.x.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->q_y.p, hp.y.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->q_n.p, hp.n.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->q_status.p, hp.status.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess && w) {
+        e = c->h_wext.reserve(sizeof(double) * (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_wext.p, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+      }
+    }
+    if (e != cudaSuccess) rc = plo_fail(c, PLO_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  }
+  if (rc == PLO_OK) {
+    c->host_drpm_only = drpm_only;
+    c->host_w = (drpm_only && w && n > 0) ? c->h_wext.as<double>() : nullptr;
+    rc = plo_launch_init_state(c, nullptr);
+    if (rc == PLO_OK) rc = plo_launch_reduce_solve(c, false);
+    c->host_drpm_only = false;
+    c->host_w = nullptr;
+  }
+  // the staging copies above are from pageable host memory: done when they return.  Put the context's own counts back.
+  if (c->counts_saved.p) cudaMemcpyAsync(c->counts.p, c->counts_saved.p, sizeof(DevCounts), cudaMemcpyDeviceToDevice, c->stream);
+  if (rc == PLO_OK) rc = fetch_state(c);
+  c->prm = saved_prm;
+  c->dprm = saved_dprm;
+  c->m_raw = saved_m;
+  c->projected = false;
+  c->prev_valid = false;
+  c->hooks_valid = false;
+  if (rc == PLO_OK) memcpy(delta, c->h_state->delta, sizeof(double) * 16);
+  return rc;
+}
+}  // namespace
+
+int plo_solve_ls_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, int64_t n, double threshold,
+                      double delta[16], int32_t* rank) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  if (!(threshold >= 0.0 && threshold < 0.5)) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_ls_host: threshold must be in [0, 0.5)");
+  plo_params p = c->prm;
+  p.solver = PLO_SOLVER_LS;
+  p.ls_threshold = threshold;
+  PLO_TRY(solve_host_pairs(c, "plo_solve_ls_host", src, ref, nrm, nullptr, n, p, false, delta));
+  if (rank) *rank = c->h_state->rank;
+  return PLO_OK;
+}
+
+int plo_solve_ransac_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, int64_t n, const plo_params* ransac,
+                          double delta[16], double probs[6], int64_t* inliers, int32_t* hypotheses) {
+  if (!c || !ransac) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_ransac_host: NULL argument");
+  plo_params p = *ransac;
+  p.solver = PLO_SOLVER_RANSAC;
+  if (p.ransac_final != PLO_FINAL_LS && p.ransac_final != PLO_FINAL_WLS && p.ransac_final != PLO_FINAL_DRPM)
+    return plo_fail(c, PLO_ERR_UNSUPPORTED, "plo_solve_ransac_host: final_solve_method must be LS, Weighted LS or DRPM");
+  if (p.ransac_final == PLO_FINAL_LS && !(p.ls_threshold >= 0.0 && p.ls_threshold < 0.5))
+    return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_solve_ransac_host: ls_threshold must be in [0, 0.5)");
+  PLO_TRY(solve_host_pairs(c, "plo_solve_ransac_host", src, ref, nrm, nullptr, n, p, false, delta));
+  if (probs) memcpy(probs, c->h_state->probs, sizeof(double) * 6);
+  if (inliers) *inliers = c->h_state->ransac_best;
+  if (hypotheses) *hypotheses = c->h_state->ransac_iters;
+  return PLO_OK;
+}
+
+int plo_solve_drpm_host(plo_ctx* c, const double* src, const double* ref, const double* nrm, const double* w, int64_t n,
+                        double threshold, double stdev_points, double stdev_normals, double delta[16], double probs[6]) {
+  if (!c) return PLO_ERR_INVALID_ARG;
+  plo_params p = c->prm;
+  p.solver = PLO_SOLVER_WLS;
+  p.weight_mode = PLO_W_UNIT;
+  p.drpm_threshold = threshold;
+  p.drpm_stdev_points = stdev_points;
+  p.drpm_stdev_normals = stdev_normals;
+  PLO_TRY(solve_host_pairs(c, "plo_solve_drpm_host", src, ref, nrm, w, n, p, true, delta));
+  if (probs) memcpy(probs, c->h_state->probs, sizeof(double) * 6);
   return PLO_OK;
 }
 

@@ -97,6 +97,8 @@ struct DevParams {
   double ransac_min_inliers_pct;
   double drpm_threshold, drpm_sp2, drpm_sn2;
   unsigned long long ransac_seed;
+  int ext_weights;       // the pair weights come from the caller (host-vector solver entry points): no Huber/exp evaluation, no normalisation
+  int pad_ext;
 };
 
 // ---------------------------------------------------------------------------------
@@ -165,6 +167,9 @@ struct plo_ctx {
   DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
   DevBuf ransac_mind, partials2;                              // RANSAC FPS distances, DRPM noise partials
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
+  DevBuf h_wext, counts_saved;       // host-vector LS / RANSAC / DRPM entry points: caller weights, the context's own counts
+  const double* host_w = nullptr;    // != nullptr while such a call runs with caller weights
+  bool host_drpm_only = false;       // plo_solve_drpm_host: DRPM tail without the RANSAC front
   DevState* h_state = nullptr;       // pinned
   DevCounts* h_counts = nullptr;     // pinned
 
@@ -227,6 +232,8 @@ int plo_frontend_fetch_counts(plo_ctx* c, int64_t out7[7]);
 int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);
 int plo_reserve_query_buffers(plo_ctx* c, bool hooks);
+int plo_launch_imls_height(plo_ctx* c, const float* d_pts6, int n, double* d_height, int* d_ok);
+int plo_launch_compute_normal(plo_ctx* c, const double* d_pts3, int n, double* d_out);
 // ---- p2plane_solve.cu -------------------------------------------------------------
 int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long cond_handle = 0ull);
 int plo_reserve_solver_buffers(plo_ctx* c);

@@ -161,8 +161,30 @@ int main(int argc, char** argv) {
                            cfg.num("RANSAC", "huber_threshold", 0.648), cfg.raw("RANSAC", "final_solve_method", "DRPM"),
                            (int)cfg.num("RANSAC", "max_iterations", 5000), cfg.num("RANSAC", "min_inliers_percentage", 0.95),
                            cfg.num("RANSAC", "DRPM_threshold", 0.05), cfg.num("RANSAC", "DRPM_stdev_points", 0.02),
-                           cfg.num("RANSAC", "DRPM_stdev_normals", 0.05));
-    const bool host_vectors = solve_method == "WeightedLS_CUDA" || solve_method == "Weighted LS";
+                           cfg.num("RANSAC", "DRPM_stdev_normals", 0.05),
+                           cfg.num("RANSAC", "LS_threshold", cfg.num("LS", "threshold", 0.02)));
+    // solveMotionEstimationProblem(), src/laser_odometry.cpp:173-275, for the stepped mode: the reference's own
+    // dispatch on the config string, each branch with the reference's argument list on std::vector<Vector3d>
+    auto solveMotionEstimationProblem = [&](std::vector<Vector3d>& in_cloud_vec, std::vector<Vector3d>& ref_cloud_vec,
+                                            std::vector<Vector3d>& ref_normal, Matrix4d& deltaTrans) -> bool {
+      plo_ctx* ctx = matcher.context();
+      if (solve_method == "WeightedLS_CUDA" || solve_method == "Weighted LS") {
+        std::vector<double> no_weights;
+        return plo::SolveMotionEstimationProblemWeightedLS_CUDA(ctx, in_cloud_vec, ref_cloud_vec, ref_normal, deltaTrans, no_weights, "");
+      }
+      if (solve_method == "LS" || solve_method == "LS_CUDA")                                           // :190-197
+        return plo::SolveMotionEstimationProblemLS_CUDA(ctx, in_cloud_vec, ref_cloud_vec, ref_normal, deltaTrans, "",
+                                                        cfg.num("LS", "threshold", 0.02));
+      if (solve_method == "RANSAC")                                                                    // :199-226
+        return plo::SolveMotionEstimationProblemRANSAC_CUDA(
+            ctx, in_cloud_vec, ref_cloud_vec, ref_normal, deltaTrans, "", (int)cfg.num("RANSAC", "max_iterations", 5000),
+            cfg.num("RANSAC", "distance_threshold", 0.8), cfg.num("RANSAC", "min_inliers_percentage", 0.95),
+            cfg.num("RANSAC", "huber_threshold", 0.648), cfg.raw("RANSAC", "final_solve_method", "DRPM"),
+            cfg.num("RANSAC", "LS_threshold", cfg.num("LS", "threshold", 0.02)), cfg.num("RANSAC", "DRPM_threshold", 0.05),
+            cfg.num("RANSAC", "DRPM_stdev_points", 0.02), cfg.num("RANSAC", "DRPM_stdev_normals", 0.05));
+      std::cerr << "Invalid SOLVE_METHOD!" << std::endl;                                               // :271
+      return false;
+    };
 
     std::ofstream poses(argv[3]);
     Matrix4d prevLaserPose;   // :48-57 globals
@@ -192,11 +214,7 @@ int main(int argc, char** argv) {
               ref_normal.push_back({{p.normal_x, p.normal_y, p.normal_z}});
             }
             Matrix4d deltaTrans;
-            std::vector<double> no_weights;
-            bool flag = host_vectors
-                            ? plo::SolveMotionEstimationProblemWeightedLS_CUDA(matcher.context(), in_cloud_vec, ref_cloud_vec,
-                                                                               ref_normal, deltaTrans, no_weights, "")   // :609
-                            : matcher.solveMotionEstimationProblem(deltaTrans);   // LS / RANSAC on the resident pairs
+            bool flag = solveMotionEstimationProblem(in_cloud_vec, ref_cloud_vec, ref_normal, deltaTrans);   // :609
             if (!flag) break;                                                   // :611-616
             rPose = deltaTrans * rPose;                                         // :619
             ++iters;

@@ -67,26 +67,26 @@ class IMLSICPMatcher:
         return dict(in_cloud=pr["src_xyz"], out_cloud=pr["ref_xyz"], out_normal=pr["ref_n"], src_idx=pr["src_idx"],
                     counters=st["counters"], n_source=st["n_source"])
 
-    def ImplicitMLSFunction(self, x, normal):
-        """src/imls_icp.cpp:301-483 for one point: returns (ok, height).  Goes through the same
-        kernel as the batch path (a one-point source); the 1-NN gates of ProjSourcePtToSurface
-        are part of that kernel, so `ok` is False for a point the matcher would drop earlier."""
-        rec = np.zeros((1, 12), np.float32)
-        rec[0, 0:3] = x
-        rec[0, 4:7] = normal
-        saved = getattr(self.ctx, "_keep_s", None)
-        self.ctx.set_source(rec)
-        self.ctx.project(np.eye(4), hooks=True, stats=False)
-        q = self.ctx.query_results()
-        if saved is not None:
-            self.ctx.set_source(saved)
-        ok = int(q["status"][0]) == 0 and bool(np.isfinite(q["height"][0]))
-        return ok, float(q["height"][0])
+    def ImplicitMLSFunction(self, x, normal=None):
+        """bool ImplicitMLSFunction(PointType& x, double& height), include/imls_icp.h:75-76, src/imls_icp.cpp:301-483:
+        returns (ok, height).  `x`: the (already transformed) point xyz with `normal`, or a 6-vector / (n, 6) batch
+        (then arrays come back).  No 1-NN gates here -- those are ProjSourcePtToSurface's."""
+        a = np.asarray(x, np.float32)
+        if normal is not None:
+            a = np.concatenate([a.reshape(-1, 3), np.asarray(normal, np.float32).reshape(-1, 3)], axis=1)
+        single = a.size == 6
+        h, ok = self.ctx.imls_height(a.reshape(-1, 6))
+        return (bool(ok[0]), float(h[0])) if single else (ok, h)
 
-    def ComputeNormal(self):
-        """src/imls_icp.cpp:753-794 evaluated for every target point (n, 3) — the normals the
-        matcher uses (delivered ones when get_normals.enabled)."""
-        return self.ctx.target_normals()
+    def ComputeNormal(self, nearPoints=None):
+        """Eigen::Vector3d ComputeNormal(std::vector<Eigen::Vector3d>& nearPoints), include/imls_icp.h:84,
+        src/imls_icp.cpp:753-794: unit eigenvector of the smallest eigenvalue of the population covariance (no sign
+        disambiguation, like the reference).  Without an argument: the normals the matcher uses for every target
+        point, (n, 3) -- the delivered ones when get_normals.enabled, else this function over each point's
+        search_number_normal neighbours (oriented +z, deviation D2)."""
+        if nearPoints is None:
+            return self.ctx.target_normals()
+        return self.ctx.compute_normal(nearPoints)
 
     # ---- include/imls_icp.h:86-88 --------------------------------------------------------
     def Match(self, T0=None):

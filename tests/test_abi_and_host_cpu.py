@@ -98,6 +98,22 @@ def test_config_flattening_and_rejections(tmp_path):
         assert msg in str(e.value)
 
 
+def test_ransac_final_ls_uses_its_own_threshold():
+    """src/laser_odometry.cpp:205: the trim fraction of the final "LS" inside RANSAC is solve_method.RANSAC.LS_threshold,
+    not solve_method.LS.threshold (the two keys differ in a config.json that says so)."""
+    import plo_b200 as plo
+    cfg = plo.config.load_config()
+    sm = cfg["laser_odometry"]["solve_method"]
+    sm["LS"]["threshold"], sm["RANSAC"]["LS_threshold"] = 0.1, 0.05
+    sm["method"], sm["RANSAC"]["final_solve_method"] = "RANSAC", "LS"
+    assert plo.config.params_from_config(cfg).ls_threshold == 0.05
+    del sm["RANSAC"]["LS_threshold"]
+    assert plo.config.params_from_config(cfg).ls_threshold == 0.1      # absent: fall back
+    sm["RANSAC"]["LS_threshold"] = 0.05
+    sm["method"] = "LS"
+    assert plo.config.params_from_config(cfg).ls_threshold == 0.1
+
+
 def test_tum_pose_format(tmp_path):
     T = plo.synth.scenes.pose_matrix([1.5, -2.25, 0.125], yaw_deg=90)
     f = tmp_path / "poses.txt"

@@ -767,6 +767,109 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
 
 
+def test_host_vector_solver_entry_points(oracle_mod):
+    """SolveMotionEstimationProblem{LS,RANSAC,DRPM} with the reference's shape (include/solver.h:84-90, :100-114,
+    :129-139): host vectors in, 4x4 out, against the oracle's restatements and against the same solvers run on the
+    device-resident pairs; the dispatcher accepts the reference's strings; the context survives such a call."""
+    pair = W.hdl64_pair(max_source=20000)
+    ctx, orc = _both(oracle_mod, pair.target, pair.source)
+    ctx.project(np.eye(4))
+    pr = ctx.pairs()
+    s, d, n = (pr[k].astype(np.float64) for k in ("src_xyz", "ref_xyz", "ref_n"))
+    # LS (trimmed)
+    ctx.set_params(plo.default_params(solver=1))
+    ctx.project(np.eye(4))
+    D_res, _ = ctx.solve_ls()
+    for thr in (0.02, 0.1):
+        Dh, rank = ctx.solve_ls_host(s, d, n, thr)
+        assert rank == 6 and np.abs(Dh - oracle_mod.solve_ls(s, d, n, thr)).max() < 1e-9
+        if thr == 0.02:
+            assert np.abs(Dh - D_res).max() < 1e-10
+    # RANSAC with each final stage; a second parameter set that needs several hypotheses
+    for final in (0, 1, 2):
+        for kw in (dict(ransac_final=final), dict(ransac_final=final, ransac_min_inliers_percentage=0.9999, ransac_max_iterations=7,
+                                                   ransac_seed=12345, ransac_distance_threshold=0.05, ls_threshold=0.05)):
+            Dh, info = ctx.solve_ransac_host(s, d, n, plo.default_params(**kw))
+            ok, Do = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(solver=2, **kw))
+            assert ok and np.abs(Dh - Do).max() < 1e-9, (final, kw)
+            assert info["hypotheses"] == (7 if len(kw) > 1 else info["hypotheses"]) and info["inliers"] > 0
+    # DRPM on caller weights: unit, the RANSAC-final weights (normalised to sum 1), and un-normalised ones
+    idx, w = oracle_mod.ransac_weights(s, d, n)
+    rng = np.random.default_rng(3)
+    for ss, dd, nn, ww in ((s, d, n, None), (s[idx], d[idx], n[idx], w), (s, d, n, rng.uniform(0.1, 3.0, s.shape[0]))):
+        Dh, probs = ctx.solve_drpm_host(ss, dd, nn, ww)
+        Do, po = oracle_mod.solve_drpm(ss, dd, nn, ww)
+        assert np.abs(Dh - Do).max() < 1e-9 and np.abs(probs - po).max() < 1e-9
+    # the dispatcher of src/laser_odometry.cpp:173-275 with the reference's strings
+    cfg = plo.config.load_config()
+    sm = cfg["laser_odometry"]["solve_method"]
+    sm["LS"]["threshold"], sm["RANSAC"]["LS_threshold"], sm["RANSAC"]["final_solve_method"] = 0.1, 0.05, "LS"
+    ok, D1 = plo.solver.solveMotionEstimationProblem("LS", s, d, n, ctx=ctx, cfg=cfg)
+    assert ok and np.abs(D1 - oracle_mod.solve_ls(s, d, n, 0.1)).max() < 1e-9
+    ok, D2 = plo.solver.solveMotionEstimationProblem("RANSAC", s, d, n, ctx=ctx, cfg=cfg)
+    okr, Do = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(solver=2, ransac_final=0, ls_threshold=0.05))
+    assert ok and okr and np.abs(D2 - Do).max() < 1e-9             # the trim fraction is RANSAC.LS_threshold, not LS.threshold
+    ok, D3 = plo.solver.solveMotionEstimationProblem("Weighted LS", s, d, n, ctx=ctx, cfg=cfg)
+    assert ok and np.abs(D3 - oracle_mod.solve_wls(s, d, n)).max() < 1e-10
+    for bad in ("Ceres", "ICP", "Teaser", "nonsense"):
+        with pytest.raises(ValueError):
+            plo.solver.solveMotionEstimationProblem(bad, s, d, n, ctx=ctx, cfg=cfg)
+    # coordinates that float32 cannot hold are refused, empty input is not an error of the call
+    with pytest.raises(plo.PloError):
+        ctx.solve_ls_host(s + 1e-9, d, n)
+    # the context still registers (its clouds are untouched, the projection state was dropped)
+    ctx.set_params(plo.default_params())
+    Tg, sg = ctx.register()
+    To, so = orc.register()
+    assert sg["iters"] == so["iters"] and _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+
+
+def test_imls_function_and_compute_normal_entry_points(oracle_mod):
+    """bool ImplicitMLSFunction(PointType&, double&) and Vector3d ComputeNormal(vector<Vector3d>&)
+    (include/imls_icp.h:75-76, :84) as stand-alone calls: heights bitwise equal to those the projection computes
+    for the points it keeps, defined (and finite) for points the projection drops at its 1-NN gates, `false` exactly
+    where fewer than 3 neighbours are usable; normals against the oracle and numpy's eigh (sign-free)."""
+    pair = W.planetary_pair()                       # sparse: every drop reason occurs
+    T = pair.T_gt
+    ctx, orc = _both(oracle_mod, pair.target, pair.source[::4], h=0.6)
+    ctx.project(T, hooks=True)
+    q = ctx.query_results()
+    o = orc.project(T, hooks=True)
+    src = pair.source[::4]
+    fin = np.isfinite(src[:, 0:3]).all(axis=1)
+    src = src[fin]
+    x = (src[:, 0:3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    m = plo.IMLSICPMatcher(ctx=ctx)
+    ok, h = m.ImplicitMLSFunction(x, src[:, 4:7])
+    kept = q["status"] == 0
+    assert kept.sum() > 1000 and ok[kept].all() and np.array_equal(h[kept], q["height"][kept])
+    assert np.array_equal(~ok, np.isin(q["status"], [5]) | (~ok & np.isin(q["status"], [1, 2, 3, 4])))   # MLS_FAIL <=> not ok among the gated-in
+    assert (q["status"] == 5).sum() == (~ok[np.isin(q["status"], [0, 5, 6])]).sum()
+    gated = np.isin(q["status"], [2, 4]) & ok       # too far / normal constraint at the 1-NN: the IMLS function itself still answers
+    assert gated.any() and np.isfinite(h[gated]).all()
+    ok1, h1 = m.ImplicitMLSFunction(x[7], src[7, 4:7])
+    assert ok1 == bool(ok[7]) and (h1 == h[7] or not ok1)
+    # heights against the oracle where it kept the point
+    okk = o["status"] == 0
+    assert (np.abs(h[okk] - o["height"][okk]) <= HEIGHT_RTOL * np.abs(o["height"][okk]) + HEIGHT_ATOL).all()
+    # ComputeNormal
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        k = int(rng.choice([3, 10, 10, 25, 200]))
+        nrm = rng.normal(size=3)
+        nrm /= np.linalg.norm(nrm)
+        basis = np.linalg.svd(np.eye(3) - np.outer(nrm, nrm))[0][:, :2]
+        pts = rng.uniform(-50, 50, 3) + rng.uniform(-1, 1, size=(k, 2)) @ basis.T + rng.normal(0, 0.01, size=(k, 1)) * nrm
+        g = m.ComputeNormal(pts)
+        ref = oracle_mod.compute_normal(pts)
+        c = np.cov(pts.T, bias=True)
+        ev = np.linalg.eigh(c)[1][:, 0]
+        assert abs(np.linalg.norm(g) - 1) < 1e-12
+        assert min(np.abs(g - ref).max(), np.abs(g + ref).max()) < 1e-7
+        assert min(np.abs(g - ev).max(), np.abs(g + ev).max()) < 1e-7
+    assert m.ComputeNormal().shape == (ctx.n_target, 3)
+
+
 def test_settled_kernel_parity_from_candidate_tiles(oracle_mod):
     """k_project_settled (the streaming kernel of the settled iterations) is held to the same bars as the tree walk:
     with the `force_warm` knob a stepped projection leaves candidate tiles behind and the next ones consume them.
