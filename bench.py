@@ -205,6 +205,16 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    # one rank per GPU: give every rank its own slice of the host cores this job may use (8 ranks sharing one
+    # affinity mask let the enqueue threads migrate and collide: the host side is what limits the N = 8 curve)
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            allowed = sorted(os.sched_getaffinity(0))
+            per = max(1, len(allowed) // world)
+            mine = allowed[local_rank * per:(local_rank + 1) * per] or allowed
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
     # BASELINE config 5: 64 independent VLP-32C sequences (seeds 5000..5063), sequence s -> rank s mod N.  The frames
     # of this rank's shard are ray-cast here, in forked workers, BEFORE CUDA is initialised in this process.
     cfg5_sets = None
@@ -256,6 +266,13 @@ def main():
         ctx.set_source(h_src)
         return ctx.register()
 
+    def step_frame():
+        # the shape of the reference's odometry loop (src/laser_odometry.cpp:436-443, :668-670): the local map is
+        # already on the device (it was accumulated from earlier frames), only the NEW frame crosses the bus
+        ctx.set_target(d_tgt)
+        ctx.set_source(h_src)
+        return ctx.register()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -286,7 +303,7 @@ def main():
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     # roofline pass: the same steps again with a CUDA-event pair around every k_project launch (the timed
     # region above runs the loop as one CUDA graph, which cannot carry per-iteration event pairs)
-    proj_ms, proj_n = [], []
+    proj_ms, proj_n, proj_each, proj_miss = [], [], [], []
     ctx.set_profiling(True)
     with torch.cuda.stream(stream):
         for i in range(max(3, min(args.steps, 10))):
@@ -295,6 +312,8 @@ def main():
             kt = ctx.last_kernel_timings()
             proj_ms.append(kt["ms_project_mean"])
             proj_n.append(kt["n_project"])
+            proj_each.append(ctx.last_project_times())
+            proj_miss.append(ctx.last_tile_misses())
     ctx.set_profiling(False)
     torch.cuda.synchronize(dev)
     gather_ms = 0.0
@@ -326,22 +345,30 @@ def main():
     Tb, sb = ctx.register_batch([h_src] * args.steps, [h_tgt] * args.steps)
     t_stream = time.perf_counter() - t0
     barrier()
-    t_e2e = 0.0
+    t_e2e = t_full = 0.0
     for i in range(args.steps):
         with torch.cuda.stream(stream):
             flush.zero_()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        T2, st2 = step_host()                       # H2D both clouds ... D2H pose + stats (syncs inside)
+        T2, st2 = step_frame()                      # H2D of the new frame ... D2H pose + stats (syncs inside)
         t_e2e += time.perf_counter() - t0
     barrier()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        T3, st3 = step_host()                       # H2D of BOTH clouds (the 48 MB map as well) ... D2H pose + stats
+        t_full += time.perf_counter() - t0
+    barrier()
     if world > 1:
-        t = torch.tensor([t_e2e, t_stream], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_e2e, t_stream, t_full], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e, t_stream = float(t[0].item()), float(t[1].item())
+        t_e2e, t_stream, t_full = (float(x) for x in t.tolist())
     e2e_value = world * args.steps / t_stream
     e2e_sync_value = world * args.steps / t_e2e
-    assert np.array_equal(T2, T), "host-input and device-input paths disagree"
+    assert np.array_equal(T2, T) and np.array_equal(T3, T), "host-input and device-input paths disagree"
     assert all(np.array_equal(Tb[i], T) for i in range(args.steps)), "batched path disagrees"
 
     # ---- BASELINE config 5: the 64 sequences, sharded over the ranks (strong scaling: total work fixed) ----
@@ -385,21 +412,39 @@ def main():
     alg_bytes = st["pairs"] * BYTES_PER_PAIR + drops * BYTES_PER_DROP
     ms_proj = float(np.mean([m for m, n in zip(proj_ms, proj_n) if n > 0])) if any(proj_n) else float("nan")
     achieved = alg_bytes / (ms_proj * 1e-3) / 1e9
-    traffic = None
+    # per-launch figures of the two regimes of k_project (tree walk / candidate tiles): times measured live above,
+    # DRAM / L2 bytes, instructions per query and issue utilisation from the committed ncu captures of the same build
+    ncu = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_project", {}).get("dram_bytes_per_launch")
+            ncu = json.load(open(tpath)).get("k_project", {})
         except Exception:
-            traffic = None
+            ncu = {}
     iters = int(st["iters"])
+    each = np.mean(np.stack([e for e in proj_each if e.shape[0] == iters]), axis=0) if any(e.shape[0] == iters for e in proj_each) else np.zeros(0)
+    miss = proj_miss[-1] if proj_miss else np.zeros(0, np.int32)
+    regimes = {}
+    for name, sel in (("tree_walk", miss < 0), ("tiles", miss >= 0)):
+        if each.shape[0] == miss.shape[0] and sel.any():
+            ms = float(each[sel].mean())
+            regimes[name] = {"launches_per_step": int(sel.sum()), "ms_per_launch": ms, "achieved_gbs": alg_bytes / (ms * 1e-3) / 1e9,
+                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, **ncu.get(name, {})}
+            if name == "tiles":
+                regimes[name]["queries_sent_to_the_tree_per_launch"] = float(miss[sel].mean())
+    traffic = None
+    if regimes and all("dram_bytes_per_launch" in r for r in regimes.values()):
+        traffic = int(sum(r["dram_bytes_per_launch"] * r["launches_per_step"] for r in regimes.values()) / sum(r["launches_per_step"] for r in regimes.values()))
     share = ms_proj * float(np.mean(proj_n)) / (total_ms / args.steps) if world == 1 else None
-    roofline = {"bound": "hbm", "kernel": "k_project (knn + IMLS projection)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_project (knn + IMLS projection; tree walk in the first projections, candidate tiles once the pose settles)",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_proj,
                 "launches_per_step": float(np.mean(proj_n)), "share_of_step": share,
                 "timing": "CUDA events around every k_project launch, same steps repeated right after the timed region",
-                "note": "1 M-pt map (32 MB sorted) is L2-resident: DRAM traffic is far below algorithmic bytes by design"}
+                "regimes": regimes,
+                "note": "tree walk: the 1 M-pt map (32 MB sorted) is L2-resident, DRAM traffic is far below algorithmic bytes and the "
+                        "kernel is issue- / latency-bound (inst_per_query, issue_active_pct); tiles: 1 KB per query streams from HBM"}
 
     # ---- CPU baseline (oracle port, all host threads), same bytes, same process ----------
     cpu = None
@@ -458,7 +503,13 @@ def main():
                         "registration of step i (2 staging buffers, > L2 together with the index), one sync at the end",
                 "timer": "host wall clock around the call",
                 "sync_per_step": {"value": e2e_sync_value, "ms_per_step": 1e3 * t_e2e / args.steps,
-                                  "mode": "set_target + set_source + register per step, no overlap, L2 flushed between steps"}},
+                                  "h2d_bytes_per_step": n_s * 48, "d2h_bytes_per_step": 584 + 16,
+                                  "mode": "latency view, one frame at a time, L2 flushed between steps: the local map is resident on "
+                                          "the device (as after plo_map_push), index build + upload of the NEW frame from pinned host "
+                                          "memory (copy stream, behind the index build) + register + pose read-back, synchronous"},
+                "sync_per_step_full_upload": {"value": world * args.steps / t_full, "ms_per_step": 1e3 * t_full / args.steps,
+                                              "h2d_bytes_per_step": (n_t + n_s) * 48,
+                                              "mode": "the same with the 48 MB map uploaded from the host every step as well"}},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "parity": parity,

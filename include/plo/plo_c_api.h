@@ -147,6 +147,11 @@ PLO_API int plo_version(void);
 /* run everything on a caller-owned CUDA stream (cudaStream_t passed as void*) */
 PLO_API int plo_set_stream(plo_ctx* ctx, void* cuda_stream);
 PLO_API int plo_synchronize(plo_ctx* ctx);
+/* Device-resident inputs (plo_*_device, on_device batches) are read on the context's stream.  If another stream
+ * produced them, record an event there and pass it here first: the context's stream then waits for it (the Python
+ * Context does this for torch tensors).  Host inputs: the bytes are copied asynchronously when the buffer is pinned --
+ * leave it untouched until a call that returns results (plo_register, plo_get_*, plo_synchronize) has returned. */
+PLO_API int plo_stream_wait_event(plo_ctx* ctx, void* cuda_event);
 
 /* ---- parameters: IMLSICPMatcher::setParameters, src/imls_icp.cpp:146-168 --------- */
 PLO_API void plo_default_params(plo_params* p);

@@ -83,6 +83,21 @@ class Context:
         self._ck(self.L.plo_set_stream(self.h, C.c_void_p(int(raw))))
         self._stream_keep = stream
 
+    def _after_producer(self, x):
+        """A torch CUDA tensor is read by the library on the context's own stream: order that stream after the torch
+        stream that is current now (where the tensor was, or is being, produced) -- no global synchronisation."""
+        if not _is_torch_cuda(x):
+            return
+        import torch
+        cur = torch.cuda.current_stream(x.device)
+        mine = getattr(getattr(self, "_stream_keep", None), "cuda_stream", getattr(self, "_stream_keep", None))
+        if mine is not None and int(mine) == int(cur.cuda_stream):
+            return      # same stream: already ordered
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._ck(self.L.plo_stream_wait_event(self.h, C.c_void_p(int(ev.cuda_event))))
+        self._ev_keep = ev
+
     def set_tuning(self, name: str, value: int):
         """tuning / test knobs of plo_set_tuning: chunk, no_graph, force_warm"""
         self._ck(self.L.plo_set_tuning(self.h, name.encode(), int(value)))
@@ -98,11 +113,13 @@ class Context:
     def set_target(self, rec):
         p, n, stride, dev, keep = _records(rec)
         self._keep_t = keep
+        self._after_producer(rec)
         self._ck((self.L.plo_set_target_device if dev else self.L.plo_set_target)(self.h, p, n, stride))
 
     def set_source(self, rec):
         p, n, stride, dev, keep = _records(rec)
         self._keep_s = keep
+        self._after_producer(rec)
         self._ck((self.L.plo_set_source_device if dev else self.L.plo_set_source)(self.h, p, n, stride))
 
     # -- front-end (plo_frontend*) ----------------------------------------------------------
@@ -115,6 +132,7 @@ class Context:
         if _is_torch_cuda(points):
             t = points.contiguous()
             self._keep_fe = t
+            self._after_producer(t)
             n, stride = int(t.shape[0]), int(t.stride(0) * t.element_size()) if t.shape[0] else 12
             self._ck(self.L.plo_frontend_device(self.h, C.c_void_p(t.data_ptr()), n, stride, C.byref(fp), C.byref(st)))
         else:
@@ -165,6 +183,7 @@ class Context:
         move into the new frame's coordinates, the new frame is appended, the index is rebuilt on the device."""
         p, n, stride, dev, keep = _records(rec)
         self._keep_t = keep
+        self._after_producer(rec)
         T = None if T_last_curr is None else np.ascontiguousarray(T_last_curr, dtype=np.float64).reshape(16)
         fn = self.L.plo_map_push_device if dev else self.L.plo_map_push
         self._ck(fn(self.h, p, n, stride, _ptr(T), 1 if from_last_register else 0, int(max_queue), 1 if transform_normals else 0))
@@ -335,6 +354,8 @@ class Context:
             return np.zeros((0, 4, 4)), []
         dev = recs_s[0][3]
         stride = recs_s[0][2]
+        if dev:
+            self._after_producer(sources[0])
         for r in recs_s + recs_t:
             if r[3] != dev or (r[1] > 1 and r[2] != stride):
                 raise ValueError("register_batch: all clouds must live on the same side and share one stride")

@@ -185,13 +185,14 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket, &c->h_wext, &c->counts_saved,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket, &c->h_wext, &c->counts_saved, &c->batch_slots,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { c->lvl_lo[l].release(); c->lvl_hi[l].release(); }
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_batch_slots) cudaFreeHost(c->h_batch_slots);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->ev_proj) cudaEventDestroy(e);
   destroy_loop_graph(c);
@@ -226,10 +227,18 @@ int plo_set_tuning(plo_ctx* c, const char* name, int32_t value) {
   return PLO_OK;
 }
 
+int plo_stream_wait_event(plo_ctx* c, void* cuda_event) {
+  if (!c || !cuda_event) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_stream_wait_event: NULL argument");
+  PLO_CUDA(c, cudaSetDevice(c->device));
+  PLO_CUDA(c, cudaStreamWaitEvent(c->stream, static_cast<cudaEvent_t>(cuda_event), 0));
+  return PLO_OK;
+}
+
 int plo_synchronize(plo_ctx* c) {
   if (!c) return PLO_ERR_INVALID_ARG;
   PLO_CUDA(c, cudaSetDevice(c->device));
   PLO_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream) PLO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   return PLO_OK;
 }
 
@@ -262,15 +271,41 @@ int plo_set_params(plo_ctx* c, const plo_params* p) {
   return PLO_OK;
 }
 
+// copy stream + the events that order it against the main stream (created on first use)
+static int ensure_copy_stream(plo_ctx* c) {
+  if (!c->copy_stream) PLO_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    if (!c->ev_copied[b]) PLO_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+    if (!c->ev_consumed[b]) PLO_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming));
+  }
+  if (!c->ev_batch_start) PLO_CUDA(c, cudaEventCreateWithFlags(&c->ev_batch_start, cudaEventDisableTiming));
+  return PLO_OK;
+}
+
+// Host records -> staging buffer on the COPY stream, unpack / index build on the main stream behind an event: the
+// upload of a cloud overlaps whatever the main stream is still doing (set_target then set_source: the source crosses
+// the bus while the index of the target is being built).  slot 0 = target staging, 1 = source staging.
 static int stage_and_run(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride, DevBuf& stage, bool target) {
   if (n < 0 || (n > 0 && !host_pts)) return plo_fail(c, PLO_ERR_INVALID_ARG, "set cloud: bad pointer / count");
   if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "set cloud: stride must be >= 28 and a multiple of 4");
   PLO_CUDA(c, cudaSetDevice(c->device));
   if (n > 0) {
+    PLO_TRY(ensure_copy_stream(c));
+    const int b = target ? 0 : 1;
+    const void* before = stage.p;
     PLO_CUDA(c, stage.reserve((size_t)n * stride));
-    PLO_CUDA(c, cudaMemcpyAsync(stage.p, host_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    // the previous user of this staging buffer (main stream) must be done with it; a re-allocation frees synchronously
+    if (stage.p == before && c->stage_used[b]) PLO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    PLO_CUDA(c, cudaMemcpyAsync(stage.p, host_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->copy_stream));
+    PLO_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    PLO_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
   }
-  return target ? plo_build_index(c, stage.p, n, stride) : plo_upload_source(c, stage.p, n, stride);
+  const int rc = target ? plo_build_index(c, stage.p, n, stride) : plo_upload_source(c, stage.p, n, stride);
+  if (n > 0 && rc == PLO_OK) {
+    PLO_CUDA(c, cudaEventRecord(c->ev_consumed[target ? 0 : 1], c->stream));
+    c->stage_used[target ? 0 : 1] = true;
+  }
+  return rc;
 }
 
 int plo_set_target(plo_ctx* c, const void* host_pts, int64_t n, int32_t stride) {
@@ -1024,10 +1059,18 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
     return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad argument");
   if (count == 0) return PLO_OK;
   PLO_CUDA(c, cudaSetDevice(c->device));
-  DevBuf slots;
-  PLO_CUDA(c, slots.reserve(sizeof(DevState) * (size_t)count));
-  DevState* h_slots = nullptr;
-  PLO_CUDA(c, cudaMallocHost(&h_slots, sizeof(DevState) * (size_t)count));
+  // result slots (device + pinned host) live in the context and only ever grow: no allocation in a timed region
+  PLO_CUDA(c, c->batch_slots.reserve(sizeof(DevState) * (size_t)count));
+  if ((size_t)count > c->h_batch_cap) {
+    if (c->h_batch_slots) cudaFreeHost(c->h_batch_slots);
+    c->h_batch_slots = nullptr;
+    c->h_batch_cap = 0;
+    const size_t want = std::max<size_t>((size_t)count + (size_t)count / 2, 64);
+    PLO_CUDA(c, cudaMallocHost(&c->h_batch_slots, sizeof(DevState) * want));
+    c->h_batch_cap = want;
+  }
+  DevBuf& slots = c->batch_slots;
+  DevState* h_slots = c->h_batch_slots;
   int rc = PLO_OK;
   int graph_units = 0;
   // Host inputs: double-buffered staging on a second stream, so that the upload of pair i+1 overlaps
@@ -1035,29 +1078,24 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
   DevBuf* stage_t[2] = {&c->t_stage, &c->t_stage2};
   DevBuf* stage_s[2] = {&c->s_stage, &c->s_stage2};
   if (!on_device) {
-    if (stride < 28 || (stride % 4) != 0) { cudaFreeHost(h_slots); slots.release(); return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad stride"); }
+    if (stride < 28 || (stride % 4) != 0) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad stride");
     int64_t max_t = 1, max_s = 1;
     for (int i = 0; i < count; ++i) {
-      if (n_tgt[i] < 0 || n_src[i] < 0 || (n_tgt[i] > 0 && !targets[i]) || (n_src[i] > 0 && !sources[i])) {
-        cudaFreeHost(h_slots); slots.release();
+      if (n_tgt[i] < 0 || n_src[i] < 0 || (n_tgt[i] > 0 && !targets[i]) || (n_src[i] > 0 && !sources[i]))
         return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_register_batch: bad pointer / count");
-      }
       max_t = std::max(max_t, n_tgt[i]);
       max_s = std::max(max_s, n_src[i]);
     }
-    cudaError_t e = cudaSuccess;
-    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-      e = stage_t[b]->reserve((size_t)max_t * stride);
-      if (e == cudaSuccess) e = stage_s[b]->reserve((size_t)max_s * stride);
-      if (e == cudaSuccess && !c->ev_copied[b]) e = cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming);
-      if (e == cudaSuccess && !c->ev_consumed[b]) e = cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming);
+    PLO_TRY(ensure_copy_stream(c));
+    // earlier work on either stream may still use the staging buffers: drain the copy stream's view of them first
+    PLO_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int b = 0; b < 2; ++b) {
+      PLO_CUDA(c, stage_t[b]->reserve((size_t)max_t * stride));
+      PLO_CUDA(c, stage_s[b]->reserve((size_t)max_s * stride));
     }
-    if (e == cudaSuccess && !c->ev_batch_start) e = cudaEventCreateWithFlags(&c->ev_batch_start, cudaEventDisableTiming);
-    if (e == cudaSuccess && !c->copy_stream) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    // earlier work on the main stream may still read the staging buffers
-    if (e == cudaSuccess) e = cudaEventRecord(c->ev_batch_start, c->stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_batch_start, 0);
-    if (e != cudaSuccess) { cudaFreeHost(h_slots); slots.release(); return plo_fail(c, PLO_ERR_CUDA, std::string("plo_register_batch: ") + cudaGetErrorString(e)); }
+    c->stage_used[0] = c->stage_used[1] = false;   // this call orders the buffers with its own events
+    PLO_CUDA(c, cudaEventRecord(c->ev_batch_start, c->stream));
+    PLO_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_start, 0));
   }
   for (int i = 0; i < count && rc == PLO_OK; ++i) {
     if (on_device) {
@@ -1099,8 +1137,6 @@ int plo_register_batch(plo_ctx* c, int32_t count, const void* const* sources, co
       if (stats_out) fill_reg_stats(&h_slots[i], &stats_out[i], c->prm.iterations);
     }
   }
-  cudaFreeHost(h_slots);
-  slots.release();
   return rc;
 }
 

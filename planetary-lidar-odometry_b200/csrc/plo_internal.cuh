@@ -183,6 +183,10 @@ struct plo_ctx {
   // batched mode: host->device copies of pair i+1 overlap the registration of pair i
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_batch_start = nullptr;
+  bool stage_used[2] = {false, false};   // target / source staging buffer has a pending consumer event
+  DevBuf batch_slots;                    // plo_register_batch: per-unit result slots (device), pinned host mirror below
+  DevState* h_batch_slots = nullptr;
+  size_t h_batch_cap = 0;
   int body_launches = 2;   // kernels per loop iteration of the captured body
   // tuning knobs: environment read once at plo_create (PLO_CHUNK, PLO_NO_GRAPH), or plo_set_tuning
   int tune_chunk = -1;       // >= 0: chunk length of k_project_cold (0 = device-side policy)

@@ -767,6 +767,42 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     assert st["iters"] == so["iters"] and np.abs(st["rPose"] - Tg).max() < 1e-7
 
 
+def test_device_inputs_produced_on_another_stream(oracle_mod):
+    """torch CUDA tensors are passed by pointer and read on the context's own stream: the Context orders that stream
+    behind the torch stream that produced them (an event, no global synchronisation).  The clouds are produced on a
+    side stream behind a long-running kernel, with no synchronise before the library call."""
+    import torch
+    pair = W.hdl64_pair(max_source=20000)
+    orc = oracle_mod.Oracle()
+    orc.set_target(pair.target)
+    orc.set_source(pair.source)
+    To, so = orc.register()
+    dev = torch.device("cuda", 0)
+    h_t = torch.from_numpy(pair.target).pin_memory()
+    h_s = torch.from_numpy(pair.source).pin_memory()
+    side = torch.cuda.Stream(device=dev)
+    ctx = plo.Context(0)
+    big = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+    for rep in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(8):
+                big.normal_()                      # ~ms of work ahead of the uploads on the side stream
+            d_t = torch.empty_like(h_t, device=dev).fill_(float("nan"))
+            d_s = torch.empty_like(h_s, device=dev).fill_(float("nan"))
+            d_t.copy_(h_t, non_blocking=True)
+            d_s.copy_(h_s, non_blocking=True)
+            ctx.set_target(d_t)                    # current stream = side: the context waits for its event
+            ctx.set_source(d_s)
+        Tg, sg = ctx.register()
+        assert sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"], rep
+        assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M
+    # pinned host buffers: the upload runs on the copy stream while the index is built; results are the same
+    ctx.set_target(h_t)
+    ctx.set_source(h_s)
+    Th, sh = ctx.register()
+    assert np.array_equal(Th, Tg) and sh["iters"] == sg["iters"]
+
+
 def test_host_vector_solver_entry_points(oracle_mod):
     """SolveMotionEstimationProblem{LS,RANSAC,DRPM} with the reference's shape (include/solver.h:84-90, :100-114,
     :129-139): host vectors in, 4x4 out, against the oracle's restatements and against the same solvers run on the
