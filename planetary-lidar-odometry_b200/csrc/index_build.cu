@@ -619,12 +619,14 @@ int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t st
 int plo_map_push_records(plo_ctx* c, const void* dev_records, int64_t n, int32_t stride, const double* T_host_or_null,
                          bool pose_from_device, int32_t max_queue, bool transform_normals) {
   if (max_queue < 1) max_queue = 1;
+  // the new queue is worked out in locals and committed only after every step that can fail has succeeded
+  std::vector<int64_t> frames = c->map_frames;
   int64_t total = 0;
-  for (int64_t f : c->map_frames) total += f;
+  for (int64_t f : frames) total += f;
   int64_t drop = 0;
-  while ((int64_t)c->map_frames.size() + 1 > max_queue && !c->map_frames.empty()) {
-    drop += c->map_frames.front();
-    c->map_frames.erase(c->map_frames.begin());
+  while ((int64_t)frames.size() + 1 > max_queue && !frames.empty()) {
+    drop += frames.front();
+    frames.erase(frames.begin());
   }
   const int64_t keep = total - drop;
   const int64_t new_total = keep + n;
@@ -649,7 +651,15 @@ int plo_map_push_records(plo_ctx* c, const void* dev_records, int64_t n, int32_t
     k_map_append<<<blocks, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, n, vec16, dst.as<float4>() + 2 * keep);
     LAUNCH_CHECK(c);
   }
+  const int rc = plo_build_index(c, dst.p, new_total, 32);
+  if (rc != PLO_OK) {
+    // the old buffer is untouched, but the index over it is gone: the map is reset rather than left half-described
+    c->map_frames.clear();
+    c->err += " (plo_map_push: the local map was reset)";
+    return rc;
+  }
+  frames.push_back(n);
+  c->map_frames = frames;
   c->map_cur ^= 1;
-  c->map_frames.push_back(n);
-  return plo_build_index(c, dst.p, new_total, 32);
+  return PLO_OK;
 }

@@ -122,7 +122,7 @@ struct ProjectOut {
 // device-side counters of one projection (settled + cold launch); all zero between projections
 enum { CNT_CHUNK = 0, CNT_BLOCKS_DONE = 1, CNT_N_MISS = 2, CNT_MISS_CURSOR = 3, CNT_SETTLED_GROUP = 4, CNT_GROUPS_DONE = 5, CNT_N = 8 };
 
-constexpr int kGroup = 32;   // queries a warp takes at a time on the settled path
+constexpr int kGroup = 32;   // most queries a warp takes at a time on the settled path (fewer when the cloud is small, see plo_launch_project)
 
 struct LoopSync {
   int* counters;    // [CNT_N]
@@ -363,6 +363,11 @@ __device__ __forceinline__ void rank_tile(const MapView& m, TileScratch& ts, int
   __syncwarp();
 }
 
+// the eight 128-byte lines of a tile into L2, one line per lane
+__device__ __forceinline__ void prefetch_tile(const float4* tp, int lane) {
+  if (lane < kTileSlots / 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + lane * 8));
+}
+
 // One query whose tile covers its bound bD: the tile (two coalesced 512-byte loads, evict-first: the tiles stream
 // through, the map stays in L2) filtered by the same lower-bound test as a leaf, exact fp64 distances, ranks, tail.
 // Returns false when the query needs the tree after all (query_tail).
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
                                                                           DevState* __restrict__ st,
                                                                           const __grid_constant__ DevParams P,
                                                                           const __grid_constant__ ProjectOut out,
-                                                                          const __grid_constant__ LoopSync L, int chunk_arg) {
+                                                                          const __grid_constant__ LoopSync L, int chunk_arg, int group) {
   if (st->done) return;
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   // lane and the warp's scratch offset are made opaque: left to itself the compiler rematerialises them from the
@@ -454,18 +459,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
 
   if (tiles) {
     TileScratch& ts = reinterpret_cast<TileScratch&>(ws);
-    const int G = (n_src + kGroup - 1) / kGroup;
+    const int G = (n_src + group - 1) / group;
     const unsigned lt = (1u << lane) - 1u;
     const float r2f = bound_f(P.r2);
-    // ---- groups of 32 queries from their tiles ----
+    // ---- groups of `group` (<= 32) queries from their tiles ----
     while (true) {
       int g = 0;
       if (lane == 0) g = atomicAdd(&L.counters[CNT_SETTLED_GROUP], 1);
       g = __shfl_sync(PLO_FULL_MASK, g, 0);
       if (g >= G) break;
       // lane = query: transform, temporal bound, tile validity
-      const int qi = g * kGroup + lane;
-      const bool act = qi < n_src;
+      const int qi = g * group + lane;
+      const bool act = lane < group && qi < n_src;
       float xf = 0.f, yf = 0.f, zf = 0.f, nxf = 0.f, nyf = 0.f, nzf = 0.f, Df = CUDART_INF_F;
       bool valid = false;
       if (act) {
@@ -487,10 +492,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
         base = __shfl_sync(PLO_FULL_MASK, base, 0);
         if (act && !valid) __stcg(&L.miss_list[base + __popc(miss & lt)], qi);
       }
-      // warp = query, for every query of the group whose tile covers its bound
+      // warp = query, for every query of the group whose tile covers its bound.  The tiles come from HBM (they stream
+      // through, 135 MB per projection): the next query's tile is prefetched into L2 while this one is worked on
+      if (hit) prefetch_tile(out.tile_pts + (size_t)(g * group + __ffs(hit) - 1) * kTileSlots, lane);
       for (unsigned rem = hit; rem; rem &= rem - 1u) {
         const int j = __ffs(rem) - 1;
-        const int qj = g * kGroup + j;
+        const int qj = g * group + j;
+        if (rem & (rem - 1u)) prefetch_tile(out.tile_pts + (size_t)(g * group + __ffs(rem & (rem - 1u)) - 1) * kTileSlots, lane);
         const float bx = __shfl_sync(PLO_FULL_MASK, xf, j), by = __shfl_sync(PLO_FULL_MASK, yf, j), bz = __shfl_sync(PLO_FULL_MASK, zf, j);
         const float bnx = __shfl_sync(PLO_FULL_MASK, nxf, j), bny = __shfl_sync(PLO_FULL_MASK, nyf, j), bnz = __shfl_sync(PLO_FULL_MASK, nzf, j);
         const float bD = __shfl_sync(PLO_FULL_MASK, Df, j);
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   // (measured: second projection 0.41 -> 0.49 ms).
   {
     const float inflate = tiles ? PLO_TILE_INFLATE : PLO_TILE_INFLATE_ALL;
-    const int G = (n_src + kGroup - 1) / kGroup;
+    const int G = (n_src + group - 1) / group;
     const int n_static = (!tiles && store && PLO_BLOCK_RANGES > 0) ? (int)((long long)n_src * PLO_BLOCK_RANGES / 100) / chunk * chunk : 0;
     const int per_block = ((n_static + (int)gridDim.x - 1) / (int)gridDim.x + chunk - 1) / chunk * chunk;
     const int b0 = min((int)blockIdx.x * per_block, n_static), b1 = min(b0 + per_block, n_static);
@@ -524,12 +532,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
           const int i = atomicAdd(&L.counters[CNT_MISS_CURSOR], 1);
           volatile int* vl = L.miss_list;
           volatile int* vc = L.counters;
+          unsigned backoff = 64;
           while (true) {
             if (i >= n_src) { c0 = -2; break; }                  // the list cannot grow this long: nothing left for this warp
             c0 = vl[i];
             if (c0 >= 0) { vl[i] = -1; break; }                 // consumed: the slot is free for the next projection
             if (vc[CNT_GROUPS_DONE] >= G && i >= vc[CNT_N_MISS]) { c0 = -2; break; }   // every group is through and the list is shorter
-            __nanosleep(200);
+            __nanosleep(backoff);                                // idle warps poll ever more rarely: the issue slots belong to the others
+            backoff = min(backoff * 2u, 2048u);
           }
         }
         c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
@@ -784,7 +794,7 @@ struct ProjectLaunch {
   DevState* st;
   ProjectOut out;
   LoopSync sync;
-  int blocks, chunk;
+  int blocks, chunk, group;
 };
 
 template <bool PCA, bool HOOKS>
@@ -792,12 +802,12 @@ void launch_project_levels(plo_ctx* c, const ProjectLaunch& a) {
   const int T = kWarpsPerBlock * 32;
   switch (c->n_levels) {   // an empty map (n_levels == 0) never walks the tree: any instantiation does
     case 0:
-    case 1: k_project<PCA, 1, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 2: k_project<PCA, 2, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 3: k_project<PCA, 3, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 4: k_project<PCA, 4, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    case 5: k_project<PCA, 5, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
-    default: k_project<PCA, 6, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk); break;
+    case 1: k_project<PCA, 1, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
+    case 2: k_project<PCA, 2, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
+    case 3: k_project<PCA, 3, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
+    case 4: k_project<PCA, 4, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
+    case 5: k_project<PCA, 5, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
+    default: k_project<PCA, 6, HOOKS><<<a.blocks, T, 0, c->stream>>>(a.mv, a.sp, a.sn, a.dc, a.st, c->dprm, a.out, a.sync, a.chunk, a.group); break;
   }
 }
 }  // namespace
@@ -828,6 +838,12 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   const int64_t slots = (int64_t)plo_grid(c, PLO_MINB) * kWarpsPerBlock;
   a.chunk = (c->m_raw < 16 * slots) ? 1 : 0;
   if (c->tune_chunk >= 0) a.chunk = c->tune_chunk;   // tuning knob (0 = device-side policy)
+  // settled path: a warp takes `group` consecutive queries at a time (their per-query scalars one per lane); small
+  // clouds get small groups so that every warp of the grid has work (a 2 000-point source in groups of 32 would keep
+  // 63 warps busy, each answering 32 queries one after the other)
+  a.group = kGroup;
+  while (a.group > 1 && c->m_raw < (int64_t)a.group * 2 * slots) a.group >>= 1;
+  if (c->tune_group > 0) a.group = std::min(c->tune_group, kGroup);
   const int64_t warps = std::max<int64_t>(c->m_raw, 1);
   a.blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
   if (c->dprm.use_pca_normals) {

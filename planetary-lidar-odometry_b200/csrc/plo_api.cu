@@ -220,10 +220,11 @@ int plo_set_tuning(plo_ctx* c, const char* name, int32_t value) {
   if (!c || !name) return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: NULL argument");
   const std::string n(name);
   if (n == "chunk") c->tune_chunk = value;
+  else if (n == "group") c->tune_group = (value >= 1 && value <= 32 && (value & (value - 1)) == 0) ? value : 0;
   else if (n == "no_graph") c->tune_no_graph = value != 0;
   else if (n == "force_warm") c->tune_force_warm = value != 0;
   else if (n == "fuse") c->tune_fuse = value != 0;
-  else return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: unknown knob '" + n + "' (chunk, no_graph, force_warm, fuse)");
+  else return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: unknown knob '" + n + "' (chunk, group, no_graph, force_warm, fuse)");
   return PLO_OK;
 }
 
@@ -875,7 +876,7 @@ static std::vector<unsigned long long> loop_signature(const plo_ctx* c) {
   for (int l = 0; l < PLO_MAX_LEVELS; ++l) { add(c->lvl_lo[l].p); add(c->lvl_hi[l].p); }
   add(c->s_p.p); add(c->s_n.p); add(c->q_x.p); add(c->q_y.p); add(c->q_n.p); add(c->q_status.p); add(c->q_kd2.p); add(c->q_tile_pts.p); add(c->q_tile_meta.p);
   add(c->partials.p); add(c->state.p); add(c->counts.p); add(c->sync_counters.p); add(c->miss_list.p); add(c->reduce_ticket.p);
-  v.push_back((unsigned long long)c->tune_chunk); v.push_back(c->tune_fuse ? 1ull : 0ull);
+  v.push_back((unsigned long long)c->tune_chunk); v.push_back(c->tune_fuse ? 1ull : 0ull); v.push_back((unsigned long long)c->tune_group);
   add(c->ls_keys[0].p); add(c->ls_keys[1].p); add(c->ls_vals[0].p); add(c->ls_vals[1].p); add(c->ls_hist.p); add(c->ls_tot.p); add(c->ls_mask.p);
   add(c->ransac_mind.p); add(c->partials2.p); add(c->h_src.p); add(c->h_ref.p); add(c->h_nrm.p); add(c->h_w.p); add(c->blockcnt.p);
   v.push_back((unsigned long long)c->n_levels);

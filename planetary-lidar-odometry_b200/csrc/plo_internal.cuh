@@ -189,6 +189,7 @@ struct plo_ctx {
   size_t h_batch_cap = 0;
   int body_launches = 2;   // kernels per loop iteration of the captured body
   // tuning knobs: environment read once at plo_create (PLO_CHUNK, PLO_NO_GRAPH), or plo_set_tuning
+  int tune_group = 0;        // > 0: queries per warp and fetch on the settled path (power of two <= 32)
   int tune_chunk = -1;       // >= 0: chunk length of k_project_cold (0 = device-side policy)
   bool tune_no_graph = false;   // enqueue-all loop instead of the conditional graph (ncu cannot profile kernel nodes of such graphs)
   bool tune_fuse = true;        // resident weighted-LS loop: reduce + solve + loop tail in one launch (PLO_FUSE=0: the two stand-alone kernels)

@@ -118,6 +118,37 @@ def _frontend_golden():
     return g, dict(n_scans=int(g["n_scans"]), plane_distance_threshold=float(g["plane_distance_threshold"]))
 
 
+def test_frontend_golden_normals_against_numpy_eigh_every_point():
+    """Independent of the oracle and of the CUDA path (which mirror each other statement by statement): EVERY normal
+    of the golden front-end output against a float64 numpy.linalg.eigh of its 3 x 7 window (src/scan_registration.cpp
+    :158-229: 7 consecutive points of the point's own ring and of the rings below / above around their nearest
+    point), rebuilt here from ring ids alone.  The float32 PCA of the path agrees to 1e-6 on |cos| for all of them."""
+    g, kw = _frontend_golden()
+    pts, rec, ev, src = g["points"], g["records"], g["eigenvalues"], g["src_index"]
+    ang = np.degrees(np.arctan(pts[:, 2] / np.hypot(pts[:, 0], pts[:, 1])))
+    rid = np.floor((ang + 15) / 2 + 0.5).astype(int)          # VLP-16 ring rule, src/scan_registration.cpp:948-950
+    rings = {i: pts[rid == i] for i in range(16)}
+    ok = np.nonzero(ev[:, 0] > 0)[0]
+    assert len(ok) > 500
+    checked, worst = 0, 0.0
+    for k in ok:
+        q, i = rec[k, 0:3], rid[src[k]]
+        own = rings[i]
+        j = int(np.nonzero((own == q).all(axis=1))[0][0])
+        rows = [own[j - 3:j + 4]]
+        for nbr in (i - 1, i + 1):
+            cl = rings[nbr]
+            nn = int(np.argmin(((cl - q) ** 2).sum(axis=1)))
+            rows.append(cl[nn - 3:nn + 4])
+        P = np.concatenate(rows).astype(np.float64)
+        assert P.shape == (21, 3), k                               # a point with a normal has three complete windows
+        w, V = np.linalg.eigh(np.cov(P.T))
+        worst = max(worst, abs(abs(V[:, 0] @ rec[k, 4:7]) - 1))
+        assert np.allclose(w[::-1], ev[k], rtol=5e-3, atol=1e-7), k
+        checked += 1
+    assert checked == len(ok) and worst < 1e-6, (checked, worst)
+
+
 def test_frontend_oracle_reproduces_golden(oracle_mod):
     g, kw = _frontend_golden()
     r = oracle_mod.frontend(g["points"], oracle_mod.frontend_default_params(**kw))

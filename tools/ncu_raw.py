@@ -1,19 +1,53 @@
-"""Key metrics of `ncu --page raw --csv` exports, one column per file.  usage: ncu_raw.py a_raw.csv b_raw.csv ..."""
-import csv, sys
-KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
-        "l1tex__t_bytes.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_lsu.sum"]
+"""Key metrics of `ncu --page raw --csv` exports (one kernel launch per file), one column per file.
+usage: ncu_raw.py a_raw.csv b_raw.csv ...            table on stdout
+       ncu_raw.py --json queries name=a_raw.csv ...  per-launch figures for profiles/roofline_traffic.json"""
+import csv, json, sys
+
+KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 STALL = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio"
 STALLS = ["long_scoreboard", "no_instruction", "wait", "short_scoreboard", "membar", "lg_throttle", "math_pipe_throttle", "barrier",
-          "branch_resolving", "not_selected", "dispatch_stall", "mio_throttle", "imc_miss", "drain", "sleeping", "tex_throttle", "selected"]
-cols = []
-for f in sys.argv[1:]:
-    rows = list(csv.reader(open(f)))
-    cols.append((f, dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))))
-print(" " * 58 + "".join(f"{c[0].split('/')[-1][:22]:>24s}" for c in cols))
-for k in ["Kernel Name"] + KEYS + [STALL % s for s in STALLS]:
-    if any(k in c[1] for c in cols):
-        print(f"{k.replace('smsp__average_warps_issue_stalled_','stall ').replace('_per_issue_active.ratio',''):58s}" +
-              "".join(f"{c[1].get(k, '-')[:22]:>24s}" for c in cols) + "  " + cols[0][2].get(k, ""))
+          "branch_resolving", "not_selected", "dispatch_stall", "mio_throttle", "imc_miss", "drain", "selected"]
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3}
+
+
+def load(path):
+    rows = list(csv.reader(open(path)))
+    return dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+
+
+def val(d, u, k):
+    """metric in base units (bytes, microseconds, plain numbers)"""
+    if k not in d or d[k] in ("", "n/a"):
+        return None
+    return float(d[k].replace(",", "")) * SCALE.get(u.get(k, ""), 1.0)
+
+
+if sys.argv[1] == "--json":
+    nq = float(sys.argv[2])
+    out = {}
+    for spec in sys.argv[3:]:
+        name, path = spec.split("=", 1)
+        d, u = load(path)
+        inst = val(d, u, "smsp__inst_executed.sum")
+        issue = val(d, u, "smsp__issue_active.avg.pct_of_peak_sustained_active") or val(d, u, "smsp__issue_active.avg.pct")
+        out[name] = {"dram_bytes_per_launch": int(val(d, u, "dram__bytes_read.sum") + val(d, u, "dram__bytes_write.sum")),
+                     "l2_bytes_per_launch": int(val(d, u, "lts__t_bytes.sum")), "inst_per_query": round(inst / nq, 1),
+                     "issue_active_pct": None if issue is None else round(issue, 1),
+                     "l1_hit_pct": round(val(d, u, "l1tex__t_sector_hit_rate.pct"), 1), "l2_hit_pct": round(val(d, u, "lts__t_sector_hit_rate.pct"), 1),
+                     "warps_active_pct": round(val(d, u, "sm__warps_active.avg.pct_of_peak_sustained_active"), 1),
+                     "ncu_duration_us_cold_cache": round(val(d, u, "gpu__time_duration.sum"), 1), "capture": path.split("/")[-1]}
+    print(json.dumps({"k_project": out, "note": "ncu --set full --clock-control none, one launch per regime, caches cold and launches "
+                                               "serialised under the profiler (tools/ncu_kproj.sh); bytes and instructions per launch"}, indent=1))
+    sys.exit(0)
+
+cols = [(f,) + load(f) for f in sys.argv[1:]]
+print(" " * 50 + "".join(f"{c[0].split('/')[-1].replace('_raw.csv', '')[:20]:>22s}" for c in cols))
+for k in KEYS + [STALL % s for s in STALLS]:
+    vals = [val(c[1], c[2], k) for c in cols]
+    if any(v is not None for v in vals):
+        name = k.replace("smsp__average_warps_issue_stalled_", "stall ").replace("_per_issue_active.ratio", "")
+        print(f"{name[:50]:50s}" + "".join(f"{'-' if v is None else format(v, '.4g'):>22s}" for v in vals))
