@@ -427,36 +427,26 @@ __device__ __forceinline__ bool tile_query(const MapView& m, const DevParams& P,
 //   is its own ready flag: -1 until written, reset by its consumer), so the latency-bound walks of the few misses
 //   hide behind the streaming of the many hits.
 // Every per-query result is bitwise the same whichever path produced it.
-template <bool PCA, int LEVELS, bool HOOKS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const __grid_constant__ MapView m,
-                                                                          const float4* __restrict__ sp,
-                                                                          const float4* __restrict__ sn,
-                                                                          const DevCounts* __restrict__ counts,
-                                                                          DevState* __restrict__ st,
-                                                                          const __grid_constant__ DevParams P,
-                                                                          const __grid_constant__ ProjectOut out,
-                                                                          const __grid_constant__ LoopSync L, int chunk_arg, int group) {
-  if (st->done) return;
-  __shared__ WarpScratch s_ws[kWarpsPerBlock];
-  // lane and the warp's scratch offset are made opaque: left to itself the compiler rematerialises them from the
-  // special registers ~40 times per query (S2R + shifts: 6 % of the kernel's instructions)
-  int lane = threadIdx.x & 31;
-  unsigned ws_ofs = (threadIdx.x >> 5) * (unsigned)sizeof(WarpScratch);
-  asm volatile("" : "+r"(lane), "+r"(ws_ofs));
-  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(reinterpret_cast<char*>(s_ws) + ws_ofs);
-  const int use_prev = st->use_prev;
-  const bool store = st->warm != 0;   // the pose is settling: short chunks, block-local ranges, tiles left behind
-  const bool tiles = use_prev && st->tiles_ready;
-  const int chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
-  const int n_src = counts->n_source;
-  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
-  // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
-  __shared__ double T[12];
-  __shared__ int s_next;
-  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
-  if (threadIdx.x == 0) s_next = 0;
-  __syncthreads();
+// the loop-state values one projection works with (read once per projection, warp-uniform)
+struct ProjState {
+  int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds
+  bool store;     // the pose is settling: short chunks, block-local ranges, tiles left behind
+  bool tiles;     // every query has a tile: settled path first, the tree walk only for its misses
+  int chunk;
+};
 
+// One projection by the calling block (all blocks of the persistent grid call it): see k_project.
+// T: rPose rows in shared memory; s_next: the block's chunk counter in shared memory, zero on entry.
+template <bool PCA, int LEVELS, bool HOOKS>
+__device__ __forceinline__ void project_phase(const MapView& m, const float4* __restrict__ sp, const float4* __restrict__ sn,
+                                              const DevParams& P, const ProjectOut& out, const LoopSync& L, const ProjState ps,
+                                              const double* __restrict__ T, int* s_next_p, int n_src, int n_tgt, int group,
+                                              WarpScratch& ws, int lane) {
+  const int use_prev = ps.use_prev;
+  const bool store = ps.store;
+  const bool tiles = ps.tiles;
+  const int chunk = ps.chunk;
+  int& s_next = *s_next_p;
   if (tiles) {
     TileScratch& ts = reinterpret_cast<TileScratch&>(ws);
     const int G = (n_src + group - 1) / group;
@@ -567,6 +557,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
     }
   }
 
+}
+
+template <bool PCA, int LEVELS, bool HOOKS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const __grid_constant__ MapView m,
+                                                                          const float4* __restrict__ sp,
+                                                                          const float4* __restrict__ sn,
+                                                                          const DevCounts* __restrict__ counts,
+                                                                          DevState* __restrict__ st,
+                                                                          const __grid_constant__ DevParams P,
+                                                                          const __grid_constant__ ProjectOut out,
+                                                                          const __grid_constant__ LoopSync L, int chunk_arg, int group) {
+  if (st->done) return;
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
+  // lane and the warp's scratch offset are made opaque: left to itself the compiler rematerialises them from the
+  // special registers ~40 times per query (S2R + shifts: 6 % of the kernel's instructions)
+  int lane = threadIdx.x & 31;
+  unsigned ws_ofs = (threadIdx.x >> 5) * (unsigned)sizeof(WarpScratch);
+  asm volatile("" : "+r"(lane), "+r"(ws_ofs));
+  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(reinterpret_cast<char*>(s_ws) + ws_ofs);
+  ProjState ps;
+  ps.use_prev = st->use_prev;
+  ps.store = st->warm != 0;
+  ps.tiles = ps.use_prev && st->tiles_ready;
+  ps.chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
+  const int n_src = counts->n_source;
+  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
+  // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
+  __shared__ double T[12];
+  __shared__ int s_next;
+  if (threadIdx.x < 12) T[threadIdx.x] = st->rPose[threadIdx.x];
+  if (threadIdx.x == 0) s_next = 0;
+  __syncthreads();
+  project_phase<PCA, LEVELS, HOOKS>(m, sp, sn, P, out, L, ps, T, &s_next, n_src, n_tgt, group, ws, lane);
+
   // ---- epilogue: the last block to get here resets the projection's counters ----
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -574,9 +598,114 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   if (atomicAdd(&L.counters[CNT_BLOCKS_DONE], 1) != (int)gridDim.x - 1) return;
   __threadfence();
   const int it = st->iters;
-  if (it < 32) st->miss_hist[it] = tiles ? ((volatile int*)L.counters)[CNT_N_MISS] : -1;
-  if (store) st->tiles_ready = 1;   // every query handled by the tree walk since the reset left a tile (or an invalid mark) behind
+  if (it < 32) st->miss_hist[it] = ps.tiles ? ((volatile int*)L.counters)[CNT_N_MISS] : -1;
+  if (ps.store) st->tiles_ready = 1;   // every query handled by the tree walk since the reset left a tile (or an invalid mark) behind
   for (int i = 0; i < CNT_N; ++i) L.counters[i] = 0;
+}
+
+// ---- k_register_loop: the whole ICP loop of one registration in ONE launch ------------------------------------
+//
+// Cooperative persistent grid (every block resident).  Per iteration: projection (project_phase) | grid barrier |
+// every block reduces its fixed share of the pairs into a partial (reduce_pairs_block, the same partition and order as
+// k_reduce_solve) | grid barrier | every block sums the partials in the same fixed order and runs the 6x6 solve and
+// the loop tail on its own shared-memory copy of the loop state -- all copies stay bitwise identical, no third barrier,
+// no launch, no graph node, no host between the iterations (src/laser_odometry.cpp:524-647 resident on the device).
+// Data written by other SMs is read after a barrier whose fence invalidates the SM's L1; loads of such data never use
+// the read-only path.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* vb = bar;
+    const unsigned gen = vb[1];
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == n_blocks - 1u) {
+      vb[0] = 0u;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (vb[1] == gen) __nanosleep(40);
+    }
+    __threadfence();   // acquire side: also drops this SM's L1 lines of data other SMs have rewritten
+  }
+  __syncthreads();
+}
+
+template <bool PCA, int LEVELS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_register_loop(const __grid_constant__ MapView m,
+                                                                                const float4* __restrict__ sp,
+                                                                                const float4* __restrict__ sn,
+                                                                                const DevCounts* __restrict__ counts,
+                                                                                DevState* __restrict__ st,
+                                                                                const __grid_constant__ DevParams P,
+                                                                                const __grid_constant__ ProjectOut out,
+                                                                                const __grid_constant__ LoopSync L, int chunk_arg,
+                                                                                int group, double* __restrict__ partials,
+                                                                                unsigned* __restrict__ bar) {
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
+  __shared__ DevState s_st;   // this block's copy of the loop state (all copies evolve identically)
+  __shared__ double T[12];
+  __shared__ int s_next;
+  int lane = threadIdx.x & 31;
+  unsigned ws_ofs = (threadIdx.x >> 5) * (unsigned)sizeof(WarpScratch);
+  asm volatile("" : "+r"(lane), "+r"(ws_ofs));
+  WarpScratch& ws = *reinterpret_cast<WarpScratch*>(reinterpret_cast<char*>(s_ws) + ws_ofs);
+  // the reduce / solve phases reuse the search scratch: [warps][PLO_NSUM] warp sums, then the PLO_NSUM totals
+  double(*s_red)[PLO_NSUM] = reinterpret_cast<double(*)[PLO_NSUM]>(s_ws);
+  double* s_sum = reinterpret_cast<double*>(s_ws) + kWarpsPerBlock * PLO_NSUM;
+  static_assert(sizeof(double) * (kWarpsPerBlock + 1) * PLO_NSUM <= sizeof(WarpScratch) * kWarpsPerBlock, "scratch reuse");
+  for (int i = threadIdx.x; i < (int)(sizeof(DevState) / sizeof(int)); i += blockDim.x)
+    reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(st)[i];
+  __syncthreads();
+  const int n_src = counts->n_source;
+  const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
+#ifdef PLO_LOOP_TIMING
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(partials + (size_t)gridDim.x * PLO_NSUM);   // scratch behind the partials
+  auto stamp = [&](int it, int ph) { if (blockIdx.x == 0 && threadIdx.x == 0 && it < 16) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[it * 8 + ph] = t; } };
+#else
+  auto stamp = [](int, int) {};
+#endif
+  while (!s_st.done) {
+    const int dbg_it = s_st.iters;
+    stamp(dbg_it, 0);
+    ProjState ps;
+    ps.use_prev = s_st.use_prev;
+    ps.store = s_st.warm != 0;
+    ps.tiles = ps.use_prev && s_st.tiles_ready;
+    ps.chunk = chunk_arg > 0 ? chunk_arg : s_st.chunk;
+    if (threadIdx.x < 12) T[threadIdx.x] = s_st.rPose[threadIdx.x];
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    project_phase<PCA, LEVELS, false>(m, sp, sn, P, out, L, ps, T, &s_next, n_src, n_tgt, group, ws, lane);
+    stamp(dbg_it, 1);
+    grid_barrier(bar, gridDim.x);
+    stamp(dbg_it, 2);
+    // every query is projected.  Block 0 keeps the books while everybody reduces.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const int it = s_st.iters;
+      if (it < 32) st->miss_hist[it] = ps.tiles ? ((volatile int*)L.counters)[CNT_N_MISS] : -1;
+      for (int i = 0; i < CNT_N; ++i) L.counters[i] = 0;
+    }
+    reduce_pairs_block<kWarpsPerBlock>(out.qx, out.qy, out.qn, n_src, P, partials + (size_t)blockIdx.x * PLO_NSUM, s_red);
+    stamp(dbg_it, 3);
+    grid_barrier(bar, gridDim.x);
+    stamp(dbg_it, 4);
+    sum_block_partials(partials, (int)gridDim.x, s_sum, s_red);
+    stamp(dbg_it, 5);
+    if (threadIdx.x == 0) {
+      if (ps.store) s_st.tiles_ready = 1;
+      solve_from_sums(s_sum, &s_st, P, 1, (cudaGraphConditionalHandle)0, 0, 0);
+    }
+    __syncthreads();
+    stamp(dbg_it, 6);
+  }
+  if (blockIdx.x == 0) {
+    // miss_hist was kept in global memory by block 0; everything else comes from the shared copy
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) s_st.miss_hist[i] = st->miss_hist[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(sizeof(DevState) / sizeof(int)); i += blockDim.x)
+      reinterpret_cast<int*>(st)[i] = reinterpret_cast<const int*>(&s_st)[i];
+  }
 }
 
 // ---- PCA normals: IMLSICPMatcher::ComputeNormal (src/imls_icp.cpp:753-794) -------------
@@ -812,10 +941,8 @@ void launch_project_levels(plo_ctx* c, const ProjectLaunch& a) {
 }
 }  // namespace
 
-// One projection = one k_project launch.
-int plo_launch_project(plo_ctx* c, bool hooks) {
-  if (c->m_raw == 0) return PLO_OK;
-  ProjectLaunch a;
+namespace {
+void fill_project_launch(plo_ctx* c, ProjectLaunch& a) {
   a.mv = c->map_view();
   a.sp = c->s_p.as<float4>();
   a.sn = c->s_n.as<float4>();
@@ -846,6 +973,14 @@ int plo_launch_project(plo_ctx* c, bool hooks) {
   if (c->tune_group > 0) a.group = std::min(c->tune_group, kGroup);
   const int64_t warps = std::max<int64_t>(c->m_raw, 1);
   a.blocks = (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
+}
+}  // namespace
+
+// One projection = one k_project launch.
+int plo_launch_project(plo_ctx* c, bool hooks) {
+  if (c->m_raw == 0) return PLO_OK;
+  ProjectLaunch a;
+  fill_project_launch(c, a);
   if (c->dprm.use_pca_normals) {
     if (hooks) launch_project_levels<true, true>(c, a);
     else launch_project_levels<true, false>(c, a);
@@ -885,5 +1020,48 @@ int plo_launch_compute_normal(plo_ctx* c, const double* d_pts3, int n, double* d
   k_compute_normal<<<1, 32, 0, c->stream>>>(d_pts3, n, d_out);
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
+  return PLO_OK;
+}
+
+int plo_loop_blocks(const plo_ctx* c) {
+  const int64_t warps = std::max<int64_t>(c->m_raw, 1);
+  return (int)std::max<int64_t>(1, std::min<int64_t>((warps + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)plo_grid(c, PLO_MINB)));
+}
+
+namespace {
+template <bool PCA, int LEVELS>
+cudaError_t launch_loop_one(plo_ctx* c, ProjectLaunch& a, double* partials, unsigned* bar) {
+  auto kern = k_register_loop<PCA, LEVELS>;
+  void* args[] = {&a.mv, &a.sp, &a.sn, &a.dc, &a.st, &c->dprm, &a.out, &a.sync, &a.chunk, &a.group, &partials, &bar};
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3(a.blocks), dim3(kWarpsPerBlock * 32), args, 0, c->stream);
+}
+template <bool PCA>
+cudaError_t launch_loop_levels(plo_ctx* c, ProjectLaunch& a, double* partials, unsigned* bar) {
+  switch (c->n_levels) {
+    case 0:
+    case 1: return launch_loop_one<PCA, 1>(c, a, partials, bar);
+    case 2: return launch_loop_one<PCA, 2>(c, a, partials, bar);
+    case 3: return launch_loop_one<PCA, 3>(c, a, partials, bar);
+    case 4: return launch_loop_one<PCA, 4>(c, a, partials, bar);
+    case 5: return launch_loop_one<PCA, 5>(c, a, partials, bar);
+    default: return launch_loop_one<PCA, 6>(c, a, partials, bar);
+  }
+}
+}  // namespace
+
+// The whole weighted-LS ICP loop of one registration as ONE cooperative launch (k_register_loop).
+int plo_launch_register_loop(plo_ctx* c) {
+  ProjectLaunch a;
+  fill_project_launch(c, a);
+  PLO_CUDA(c, c->partials.reserve(sizeof(double) * PLO_NSUM * (size_t)plo_grid(c, PLO_MINB) + 8 * 8 * 16));   // (+ the PLO_LOOP_TIMING stamps)
+  if (!c->loop_barrier.p) {
+    PLO_CUDA(c, c->loop_barrier.reserve(sizeof(unsigned) * 2));
+    PLO_CUDA(c, cudaMemsetAsync(c->loop_barrier.p, 0, sizeof(unsigned) * 2, c->stream));
+  }
+  const cudaError_t e = c->dprm.use_pca_normals ? launch_loop_levels<true>(c, a, c->partials.as<double>(), c->loop_barrier.as<unsigned>())
+                                               : launch_loop_levels<false>(c, a, c->partials.as<double>(), c->loop_barrier.as<unsigned>());
+  if (e != cudaSuccess) return plo_fail(c, PLO_ERR_CUDA, std::string("k_register_loop: ") + cudaGetErrorString(e));
+  c->prev_valid = true;
+  c->launches++;
   return PLO_OK;
 }

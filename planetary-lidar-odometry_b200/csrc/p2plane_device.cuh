@@ -240,4 +240,112 @@ __device__ __noinline__ void solve_from_sums(const double* s_sum, DevState* __re
   finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
 }
 
+// ---- block-level reduction of the normal equations, shared by k_reduce_solve and k_register_loop ------------------
+// Pairs are taken in rounds of gridDim.x * blockDim.x (pair i of a round belongs to global thread i); per round every
+// value is summed over the warp by a fixed shuffle tree, rounds accumulate in order in lane 0, the warps of the block
+// are summed in order: the result depends on the launch geometry only.  The pairs were written by other SMs during the
+// same launch (k_register_loop): L2 loads.  s_red: [WARPS][PLO_NSUM] shared scratch.  Writes partial[0..PLO_NSUM).
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PLO_FULL_MASK, v, o);
+  return v;
+}
+
+template <int WARPS>
+__device__ __forceinline__ void reduce_pairs_block(const float4* qx, const float4* qy, const float4* qn, int n_src, const DevParams& P,
+                                                   double* __restrict__ partial, double (*s_red)[PLO_NSUM]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int t = 0; t < PLO_NSUM; ++t) s_red[warp][t] = 0.0;
+  const int stride = (int)(gridDim.x * blockDim.x);
+  const int rounds = (n_src + stride - 1) / stride;
+  for (int r = 0; r < rounds; ++r) {
+    const int i = r * stride + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    int status = -1;
+    double a[6] = {0, 0, 0, 0, 0, 0}, b = 0.0, w = 0.0;
+    if (i < n_src) {
+      const float4 x = __ldcg(&qx[i]);
+      status = __float_as_int(x.w);
+      if (status == PLO_PT_OK) {
+        const float4 y = __ldcg(&qy[i]);
+        const float4 nn = __ldcg(&qn[i]);
+        // getXYZ / getNormals: float32 -> double (include/common.h:51-75)
+        const double s[3] = {(double)x.x, (double)x.y, (double)x.z};
+        const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
+        const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
+        ab_row(s, d, n, a, b);
+        w = 1.0;
+        if (P.weight_mode == PLO_W_HUBER_EXP) {   // weights at the identity hypothesis (src/solver.cpp:334-364)
+          const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+          w = huber_exp_weight(I4, s, d, n, P);
+          if (w < 0.0) w = 0.0;   // not an inlier: counted as a pair, absent from the sums
+        }
+      }
+    }
+    int t = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = p; q < 6; ++q) {
+        const double v = warp_tree_sum(w * a[p] * a[q]);
+        if (lane == 0) s_red[warp][t] += v;
+        ++t;
+      }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      const double v = warp_tree_sum(w * a[p] * b);
+      if (lane == 0) s_red[warp][21 + p] += v;
+    }
+    {
+      const double v = warp_tree_sum(w), v2 = warp_tree_sum(w * b * b);
+      if (lane == 0) { s_red[warp][27] += v; s_red[warp][28] += v2; }
+    }
+#pragma unroll
+    for (int sd = 0; sd <= 6; ++sd) {   // pair count and the six drop counters
+      const int c = __popc(__ballot_sync(PLO_FULL_MASK, status == sd));
+      if (lane == 0) s_red[warp][29 + sd] += (double)c;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < PLO_NSUM) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < WARPS; ++wv) v += s_red[wv][threadIdx.x];
+    partial[threadIdx.x] = v;
+  }
+}
+
+// block partials -> s_sum[PLO_NSUM].  Warp w takes the partials w, w + #warps, ... (lane = value index: one coalesced
+// 288-byte row per partial, all of a thread's loads in flight together -- a sequential sum over 296 L2 round trips took
+// 16 us), adds them in that order, then thread t adds the warps' sums in order.  Every block that runs this on the same
+// partials gets the same bits.  s_stage: [#warps][PLO_NSUM] shared scratch (may alias s_sum's neighbourhood, not s_sum).
+__device__ __forceinline__ void sum_block_partials(const double* partials, int n_partials, double* s_sum, double (*s_stage)[PLO_NSUM]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int t = half * 32 + lane;
+    if (t < PLO_NSUM) {
+      double acc = 0.0;
+      for (int b0 = warp; b0 < n_partials; b0 += 8 * nwarps) {   // eight loads in flight, added in order
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int b = b0 + j * nwarps;
+          v[j] = (b < n_partials) ? __ldcg(&partials[(size_t)b * PLO_NSUM + t]) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+      }
+      s_stage[warp][t] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < PLO_NSUM) {
+    double acc = 0.0;
+    for (int w = 0; w < nwarps; ++w) acc += s_stage[w][threadIdx.x];
+    s_sum[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
 }  // namespace

@@ -89,57 +89,23 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_pairs(const float4* _
   block_reduce_store(acc, partials + (size_t)blockIdx.x * PLO_NSUM);
 }
 
-// block partials -> s_sum (256 threads): value t is summed by warp (t mod 8), lane-strided partial sums in a fixed order,
-// fixed shuffle tree
-__device__ __forceinline__ void sum_block_partials(const double* __restrict__ partials, int n_partials, double* s_sum) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t = warp; t < PLO_NSUM; t += 8) {
-    double v = 0.0;
-    for (int b = lane; b < n_partials; b += 32) v += __ldcg(&partials[(size_t)b * PLO_NSUM + t]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PLO_FULL_MASK, v, o);
-    if (lane == 0) s_sum[t] = v;
-  }
-  __syncthreads();
-}
-
-// Resident weighted-LS loop: reduce + solve + loop tail in ONE launch.  Every block reduces its share of the pairs as
-// k_reduce_pairs does (same order, same partials); the last block to finish sums the block partials (fixed order),
-// solves and advances the loop state (k_solve_update, stage 0) -- bitwise the same result as the two stand-alone
-// kernels, one graph node and one dependent launch less per ICP iteration.
-__global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const float4* __restrict__ qx, const float4* __restrict__ qy,
-                                                                 const float4* __restrict__ qn,
-                                                                 const DevCounts* __restrict__ counts, DevState* __restrict__ st,
-                                                                 DevParams P, double* __restrict__ partials,
-                                                                 int* __restrict__ done_ticket, cudaGraphConditionalHandle cond,
-                                                                 int use_cond) {
+// Weighted-LS loop outside k_register_loop (profiling / enqueue-all mode, graph fallback): reduce + solve + loop tail
+// in ONE launch.  Every block reduces its share of the pairs (reduce_pairs_block: the partition and order of
+// k_register_loop for the same geometry); the last block to finish sums the block partials (fixed order), solves and
+// advances the loop state -- bitwise the result of k_register_loop.
+constexpr int kFusedReduceWarps = 16;
+__global__ void __launch_bounds__(kFusedReduceWarps * 32) k_reduce_solve(const float4* __restrict__ qx, const float4* __restrict__ qy,
+                                                                         const float4* __restrict__ qn,
+                                                                         const DevCounts* __restrict__ counts, DevState* __restrict__ st,
+                                                                         DevParams P, double* __restrict__ partials,
+                                                                         int* __restrict__ done_ticket, cudaGraphConditionalHandle cond,
+                                                                         int use_cond) {
   if (st->done) {
     if (use_cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(cond, 0);
     return;
   }
-  double acc[PLO_NSUM];
-#pragma unroll
-  for (int t = 0; t < PLO_NSUM; ++t) acc[t] = 0.0;
-  const int n_src = counts->n_source;
-  const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // the Huber/exp weights are evaluated at the identity
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
-    const float4 x = __ldg(&qx[i]);
-    const int status = __float_as_int(x.w);
-    if (status != PLO_PT_OK) { acc[30 + status - 1] += 1.0; continue; }
-    const float4 y = __ldg(&qy[i]);
-    const float4 nn = __ldg(&qn[i]);
-    const double s[3] = {(double)x.x, (double)x.y, (double)x.z};
-    const double d[3] = {(double)y.x, (double)y.y, (double)y.z};
-    const double n[3] = {(double)nn.x, (double)nn.y, (double)nn.z};
-    acc[29] += 1.0;
-    double w = 1.0;
-    if (P.weight_mode == PLO_W_HUBER_EXP) {
-      w = huber_exp_weight(I4, s, d, n, P);
-      if (w < 0.0) continue;
-    }
-    accumulate_pair(acc, s, d, n, w);
-  }
-  block_reduce_store(acc, partials + (size_t)blockIdx.x * PLO_NSUM);
+  __shared__ double s_red[kFusedReduceWarps][PLO_NSUM];
+  reduce_pairs_block<kFusedReduceWarps>(qx, qy, qn, counts->n_source, P, partials + (size_t)blockIdx.x * PLO_NSUM, s_red);
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
@@ -149,7 +115,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_solve(const float4* _
   __threadfence();
   if (threadIdx.x == 0) *done_ticket = 0;
   __shared__ double s_sum[PLO_NSUM];
-  sum_block_partials(partials, (int)gridDim.x, s_sum);
+  sum_block_partials(partials, (int)gridDim.x, s_sum, s_red);
   if (threadIdx.x == 0) solve_from_sums(s_sum, st, P, 1, cond, use_cond, 0);
 }
 
@@ -345,7 +311,8 @@ __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__
     return;
   }
   __shared__ double s_sum[PLO_NSUM];
-  sum_block_partials(partials, n_partials, s_sum);
+  __shared__ double s_stage[8][PLO_NSUM];
+  sum_block_partials(partials, n_partials, s_sum, s_stage);
   if (threadIdx.x != 0) return;
   solve_from_sums(s_sum, st, P, advance_loop, cond, use_cond, stage);
 }
@@ -873,7 +840,7 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   if (advance_loop && c->tune_fuse && c->dprm.solver == PLO_SOLVER_WLS) {
     // resident weighted-LS loop: one launch (k_reduce_pairs and k_solve_update read the qx / qy / qn a projection wrote
     // in the same kernel; the projection itself may come through the read-only path here: another launch wrote it)
-    k_reduce_solve<<<g, kReduceThreads, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
+    k_reduce_solve<<<plo_loop_blocks(c), kFusedReduceWarps * 32, 0, c->stream>>>(c->q_x.as<float4>(), c->q_y.as<float4>(), c->q_n.as<float4>(),
                                                         c->counts.as<DevCounts>(), c->state.as<DevState>(), P,
                                                         c->partials.as<double>(), c->reduce_ticket.as<int>(), cond, use_cond);
     c->launches++;

@@ -160,10 +160,12 @@ int plo_create(int device, plo_ctx** out) {
     return PLO_ERR_UNSUPPORTED;
   }
   c->sm_count = prop.multiProcessorCount;
+  c->coop_ok = prop.cooperativeLaunch != 0;
   // tuning knobs from the environment, read once (plo_set_tuning overrides them later)
   if (const char* e = getenv("PLO_CHUNK")) c->tune_chunk = std::max(0, atoi(e));
   if (const char* e = getenv("PLO_NO_GRAPH")) c->tune_no_graph = atoi(e) != 0;
   if (const char* e = getenv("PLO_FUSE")) c->tune_fuse = atoi(e) != 0;
+  if (const char* e = getenv("PLO_LOOP_KERNEL")) c->tune_loop_kernel = atoi(e) != 0;
   CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   for (int i = 0; i < 4; ++i) CREATE_CUDA(cudaEventCreate(&c->ev[i]));
@@ -185,7 +187,7 @@ void plo_destroy(plo_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->t_stage, &c->t_stage2, &c->s_stage2, &c->t_praw, &c->t_nraw, &c->t_cidx, &c->blockcnt, &c->bbox, &c->keys[0], &c->keys[1],
                     &c->vals[0], &c->vals[1], &c->hist, &c->digit_total, &c->pts_sorted, &c->nrm_sorted, &c->nrm_pca, &c->pos_of_cidx,
-                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket, &c->h_wext, &c->counts_saved, &c->batch_slots,
+                    &c->s_stage, &c->s_praw, &c->s_nraw, &c->s_p, &c->s_n, &c->map_rec[0], &c->map_rec[1], &c->fe_stage, &c->fe_counts, &c->fe_blockcnt, &c->fe_kp, &c->fe_ring, &c->fe_inten, &c->fe_rp, &c->fe_rsrc, &c->fe_nn[0], &c->fe_nn[1], &c->fe_status, &c->fe_nrm, &c->fe_ev, &c->fe_rec, &c->fe_ev3, &c->fe_cand, &c->fe_src, &c->fe_keys[0], &c->fe_keys[1], &c->fe_vals[0], &c->fe_vals[1], &c->fe_hist, &c->fe_tot, &c->q_x, &c->q_y, &c->q_n, &c->q_status, &c->q_kd2, &c->q_tile_pts, &c->q_tile_meta, &c->sync_counters, &c->miss_list, &c->reduce_ticket, &c->loop_barrier, &c->h_wext, &c->counts_saved, &c->batch_slots,
                     &c->q_height, &c->q_nn1_idx, &c->q_nn1_d2, &c->q_nn_idx, &c->q_nn_d2, &c->q_stats, &c->partials, &c->state,
                     &c->counts, &c->scratch, &c->ls_keys[0], &c->ls_keys[1], &c->ls_vals[0], &c->ls_vals[1], &c->ls_hist, &c->ls_tot, &c->ls_mask, &c->ransac_mind, &c->partials2, &c->h_src, &c->h_ref, &c->h_nrm, &c->h_w};
   for (DevBuf* b : bufs) b->release();
@@ -224,7 +226,8 @@ int plo_set_tuning(plo_ctx* c, const char* name, int32_t value) {
   else if (n == "no_graph") c->tune_no_graph = value != 0;
   else if (n == "force_warm") c->tune_force_warm = value != 0;
   else if (n == "fuse") c->tune_fuse = value != 0;
-  else return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: unknown knob '" + n + "' (chunk, group, no_graph, force_warm, fuse)");
+  else if (n == "loop_kernel") c->tune_loop_kernel = value != 0;
+  else return plo_fail(c, PLO_ERR_INVALID_ARG, "plo_set_tuning: unknown knob '" + n + "' (chunk, group, no_graph, force_warm, fuse, loop_kernel)");
   return PLO_OK;
 }
 
@@ -943,6 +946,18 @@ static int enqueue_register(plo_ctx* c, const double* T0) {
   // driver refuses conditional nodes) every iteration is enqueued up front instead; kernels of
   // iterations after convergence then see the device-side `done` flag and return at once.
   // PLO_NO_GRAPH=1: enqueue-all path (ncu cannot profile kernel nodes of graphs with conditional nodes)
+  // Product path for the weighted-LS solver: the whole loop is ONE cooperative launch (k_register_loop), grid barriers
+  // between the phases of an iteration, no launch / graph node / host between iterations.
+  if (!c->profiling && !c->tune_no_graph && c->tune_loop_kernel && c->tune_fuse && c->dprm.solver == PLO_SOLVER_WLS && c->m_raw > 0 &&
+      c->coop_ok) {
+    PLO_TRY(plo_launch_register_loop(c));
+    c->projected = true;
+    c->hooks_valid = false;
+    c->graph_launched = false;
+    c->loop_kernel_launched = true;
+    return PLO_OK;
+  }
+  c->loop_kernel_launched = false;
   if (!c->profiling && c->graph_ok && !c->tune_no_graph && c->m_raw > 0) {
     if (!c->loop_exec || c->loop_sig != loop_signature(c)) {
       if (build_loop_graph(c) != 0) c->graph_ok = false;
@@ -1160,6 +1175,13 @@ int plo_last_tile_misses(plo_ctx* c, int32_t* misses, int32_t cap, int32_t* n_pr
   if (misses)
     for (int i = 0; i < n && i < cap; ++i) misses[i] = c->h_state->miss_hist[i];
   if (n_project) *n_project = n;
+  return PLO_OK;
+}
+
+// PLO_LOOP_TIMING builds only: globaltimer stamps of block 0 at the phase boundaries of k_register_loop (ns, 7 per iteration)
+int plo_debug_loop_stamps(plo_ctx* c, unsigned long long* out128) {
+  if (!c || !out128) return PLO_ERR_INVALID_ARG;
+  PLO_CUDA(c, cudaMemcpy(out128, c->partials.as<double>() + (size_t)plo_loop_blocks(c) * PLO_NSUM, 8 * 8 * 16, cudaMemcpyDeviceToHost));
   return PLO_OK;
 }
 

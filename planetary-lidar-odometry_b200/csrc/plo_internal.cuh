@@ -163,7 +163,7 @@ struct plo_ctx {
   bool projected = false;
 
   // reduction / solve
-  DevBuf partials, state, counts, scratch, reduce_ticket;
+  DevBuf partials, state, counts, scratch, reduce_ticket, loop_barrier;
   DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
   DevBuf ransac_mind, partials2;                              // RANSAC FPS distances, DRPM noise partials
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
@@ -192,9 +192,12 @@ struct plo_ctx {
   int tune_group = 0;        // > 0: queries per warp and fetch on the settled path (power of two <= 32)
   int tune_chunk = -1;       // >= 0: chunk length of k_project_cold (0 = device-side policy)
   bool tune_no_graph = false;   // enqueue-all loop instead of the conditional graph (ncu cannot profile kernel nodes of such graphs)
+  bool tune_loop_kernel = true; // resident weighted-LS loop as ONE cooperative launch (k_register_loop); PLO_LOOP_KERNEL=0: graph of launches
   bool tune_fuse = true;        // resident weighted-LS loop: reduce + solve + loop tail in one launch (PLO_FUSE=0: the two stand-alone kernels)
   bool tune_force_warm = false; // projections start in the settled regime (tiles stored / used) -- parity tests of k_project_settled
   bool graph_launched = false;   // the last enqueue_register went through the graph
+  bool loop_kernel_launched = false;   // ... through k_register_loop (one launch)
+  bool coop_ok = true;           // the device supports cooperative launches
   bool graph_ok = true;      // cleared if the driver rejects conditional nodes: falls back to enqueue-all
   bool profiling = false;
   std::vector<cudaEvent_t> ev_proj;   // 2 per loop iteration when profiling
@@ -236,6 +239,8 @@ int plo_frontend_fetch_counts(plo_ctx* c, int64_t out7[7]);
 // ---- knn_project.cu ---------------------------------------------------------------
 int plo_launch_pca_normals(plo_ctx* c);
 int plo_launch_project(plo_ctx* c, bool hooks);
+int plo_launch_register_loop(plo_ctx* c);   // the whole weighted-LS loop in one cooperative launch
+int plo_loop_blocks(const plo_ctx* c);       // blocks of the persistent projection / loop grids
 int plo_reserve_query_buffers(plo_ctx* c, bool hooks);
 int plo_launch_imls_height(plo_ctx* c, const float* d_pts6, int n, double* d_height, int* d_ok);
 int plo_launch_compute_normal(plo_ctx* c, const double* d_pts3, int n, double* d_out);
