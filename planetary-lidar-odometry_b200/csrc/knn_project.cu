@@ -122,6 +122,12 @@ struct ProjectOut {
 // device-side counters of one projection (settled + cold launch); all zero between projections
 enum { CNT_CHUNK = 0, CNT_BLOCKS_DONE = 1, CNT_N_MISS = 2, CNT_MISS_CURSOR = 3, CNT_SETTLED_GROUP = 4, CNT_GROUPS_DONE = 5, CNT_N = 8 };
 
+#ifndef PLO_TAIL_PCT
+#define PLO_TAIL_PCT 12     // last per cent of the cloud handed out in short chunks (tree walk with long chunks)
+#endif
+#ifndef PLO_TAIL_CHUNK
+#define PLO_TAIL_CHUNK 2
+#endif
 constexpr int kGroup = 32;   // most queries a warp takes at a time on the settled path (fewer when the cloud is small, see plo_launch_project)
 
 struct LoopSync {
@@ -515,6 +521,9 @@ __device__ __forceinline__ void project_phase(const MapView& m, const float4* __
     const int per_block = ((n_static + (int)gridDim.x - 1) / (int)gridDim.x + chunk - 1) / chunk * chunk;
     const int b0 = min((int)blockIdx.x * per_block, n_static), b1 = min(b0 + per_block, n_static);
     bool own_range = n_static > 0;
+    const int tail_chunk = chunk > PLO_TAIL_CHUNK ? PLO_TAIL_CHUNK : chunk;
+    const int n_long = (chunk > tail_chunk) ? (int)((long long)(n_src - n_static) * (100 - PLO_TAIL_PCT) / 100) / chunk : 0x3fffffff;   // long chunks handed out
+    const int tail0 = (chunk > tail_chunk) ? n_static + n_long * chunk : 0x7fffffff;   // first query of the short-chunk tail
     while (true) {
       int c0 = 0, c1 = 0;
       if (tiles) {
@@ -543,13 +552,20 @@ __device__ __forceinline__ void project_phase(const MapView& m, const float4* __
           c_end = b1;
           if (c0 >= b1) own_range = false;
         }
+        int len = chunk;
         if (!own_range) {
-          if (lane == 0) c0 = n_static + atomicAdd(&L.counters[CNT_CHUNK], 1) * chunk;
+          // long chunks for most of the cloud, short ones for its last PLO_TAIL_PCT %: the projection ends when the
+          // last warp finishes its last chunk, and a long chunk picked up late is 25-50 us of tail
+          if (lane == 0) {
+            const int u = atomicAdd(&L.counters[CNT_CHUNK], 1);
+            c0 = (u < n_long) ? n_static + u * chunk : tail0 + (u - n_long) * tail_chunk;
+          }
           c0 = __shfl_sync(PLO_FULL_MASK, c0, 0);
           c_end = n_src;
+          if (c0 >= tail0) len = tail_chunk;
         }
         if (c0 >= n_src) break;
-        c1 = min(c0 + chunk, c_end);
+        c1 = min(c0 + len, c_end);
       }
       Carry cy;
       cy.kf = CUDART_INF_F; cy.x = cy.y = cy.z = 0.f; cy.pos = -1;
