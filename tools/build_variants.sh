@@ -12,7 +12,7 @@ while [ $# -ge 2 ]; do
   tag="$1"; defs="$2"; shift 2
   d="$OUT/obj_$tag"; mkdir -p "$d"
   for f in plo_api index_build knn_project p2plane_solve frontend; do
-    if [ "$f" = knn_project ] || [ "$f" = p2plane_solve ] || [ ! -f "$CS/$f.o" ]; then nvcc $FLAGS $defs -c "$CS/$f.cu" -o "$d/$f.o" & else cp "$CS/$f.o" "$d/$f.o"; fi
+    if [ "$f" = knn_project ] || [ "$f" = p2plane_solve ] || [ "$f" = index_build ] || [ ! -f "$CS/$f.o" ]; then nvcc $FLAGS $defs -c "$CS/$f.cu" -o "$d/$f.o" & else cp "$CS/$f.o" "$d/$f.o"; fi
   done
   wait
   nvcc -shared -cudart static -o "$OUT/libplo_cuda_$tag.so" "$d"/*.o 2>/dev/null

@@ -44,6 +44,30 @@ if sys.argv[1] == "--json":
                                                "serialised under the profiler (tools/ncu_kproj.sh); bytes and instructions per launch"}, indent=1))
     sys.exit(0)
 
+if sys.argv[1] == "--kernels":
+    # every launch of a multi-kernel capture: duration, DRAM / L2 bytes, achieved DRAM GB/s, issue utilisation, occupancy
+    print(f"{'kernel':44s} {'n':>3s} {'us':>8s} {'dram MB':>8s} {'L2 MB':>8s} {'dram GB/s':>9s} {'issue%':>6s} {'warps%':>6s} {'L2hit%':>6s} {'regs':>4s} {'grid':>6s}")
+    for path in sys.argv[2:]:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], dict(zip(rows[0], rows[1]))
+        agg = {}
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            name = d["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")[:44]
+            us = val(d, units, "gpu__time_duration.sum")
+            dr = (val(d, units, "dram__bytes_read.sum") or 0) + (val(d, units, "dram__bytes_write.sum") or 0)
+            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, d.get("launch__registers_per_thread", ""), d.get("launch__grid_size", "")])
+            a[0] += 1; a[1] += us; a[2] += dr; a[3] += val(d, units, "lts__t_bytes.sum") or 0
+            a[4] += val(d, units, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0
+            a[5] += val(d, units, "sm__warps_active.avg.pct_of_peak_sustained_active") or 0
+            a[6] += val(d, units, "lts__t_sector_hit_rate.pct") or 0
+        tot = sum(a[1] for a in agg.values())
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            n = a[0]
+            print(f"{name:44s} {n:3d} {a[1]:8.1f} {a[2] / 1e6:8.1f} {a[3] / 1e6:8.1f} {a[2] / max(a[1], 1e-9) / 1e3:9.1f} {a[4] / n:6.1f} {a[5] / n:6.1f} {a[6] / n:6.1f} {a[7]:>4s} {a[8]:>6s}")
+        print(f"{'TOTAL ' + path.split('/')[-1]:44s} {'':3s} {tot:8.1f}")
+    sys.exit(0)
+
 cols = [(f,) + load(f) for f in sys.argv[1:]]
 print(" " * 50 + "".join(f"{c[0].split('/')[-1].replace('_raw.csv', '')[:20]:>22s}" for c in cols))
 for k in KEYS + [STALL % s for s in STALLS]:

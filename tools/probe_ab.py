@@ -16,12 +16,12 @@ else:
 import torch
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ctx = plo.Context(0)
-regs = []
+regs, idxs = [], []
 for i in range(8):
     ctx.set_target(target); ctx.set_source(source)
     flush.zero_(); torch.cuda.synchronize()
     T, rs = ctx.register()
-    if i >= 2: regs.append(ctx.last_timings()["ms_register"])
+    if i >= 2: regs.append(ctx.last_timings()["ms_register"]); idxs.append(ctx.last_timings()["ms_index_build"])
 ctx.set_profiling(True)
 kp = []
 for i in range(3):
@@ -30,5 +30,5 @@ ctx.set_profiling(False)
 misses = ctx.last_tile_misses()
 steady = ctx.time_project_kernel(T, 10)
 fp = float(np.abs(T).sum())
-print(f"[{tag}] iters {rs['iters']} pairs {rs['pairs']} fp {fp:.12f} | register ms median {np.median(regs):.4f} min {np.min(regs):.4f} | "
+print(f"[{tag}] iters {rs['iters']} pairs {rs['pairs']} fp {fp:.12f} | index build ms {np.median(idxs):.4f} | register ms median {np.median(regs):.4f} min {np.min(regs):.4f} | "
       f"k_project mean/launch {np.mean(kp):.4f} | steady (converged pose) {steady:.4f} | per launch {np.round(each, 3).tolist()} | tile misses {misses.tolist()}", flush=True)
