@@ -8,11 +8,14 @@ upload (plo_set_source) + the resident IMLS-ICP loop to convergence (plo_registe
   value        whole-job scans/s, inputs resident in HBM when the timed region starts
                (CUDA events on the context's stream, L2 flushed between steps)
   e2e          the same through the public API with pinned HOST buffers: H2D of both clouds
-               and D2H of the pose inside the timed region (host wall clock, sync inside)
-  roofline     dominant kernel (k_project): algorithmic bytes / mean launch time, the launch
-               time measured live with CUDA events inside the timed steps
+               and D2H of the pose inside the timed region (host wall clock, sync inside);
+               e2e.sync_per_step = the latency view (map resident on the device, the new frame uploaded)
+  roofline     dominant kernel (k_register_loop, the whole ICP loop in one launch): algorithmic
+               bytes / launch time, the launch time measured live with CUDA events inside the timed steps
   cpu_baseline the CPU oracle (port of the reference's algorithm; the reference itself cannot
                be compiled here) with all host threads on the same workload — rank 0, N=1 only
+  parity       SURVEY 8d gates against the oracle in the same run (neighbour sets, heights, counters, pose)
+  cfg5         BASELINE config 5: 64 independent sequences sharded over the ranks, with the hash of the pose table
   --impl reference   times that CPU path alone
 
 Multi-GPU (torchrun, one rank per GPU): every rank registers its own frame (weak scaling, units
@@ -410,41 +413,48 @@ def main():
     peak, peak_src = measured_peak()
     drops = int(st["counters"].sum())
     alg_bytes = st["pairs"] * BYTES_PER_PAIR + drops * BYTES_PER_DROP
-    ms_proj = float(np.mean([m for m, n in zip(proj_ms, proj_n) if n > 0])) if any(proj_n) else float("nan")
-    achieved = alg_bytes / (ms_proj * 1e-3) / 1e9
-    # per-launch figures of the two regimes of k_project (tree walk / candidate tiles): times measured live above,
-    # DRAM / L2 bytes, instructions per query and issue utilisation from the committed ncu captures of the same build
+    # The dominant kernel is k_register_loop: the whole ICP loop of a registration in ONE launch (7 projections here,
+    # each followed by the reduce and the solve).  Launch duration: CUDA events around it inside the timed steps
+    # (plo_last_timings).  Algorithmic bytes per launch: SURVEY 8d's 504 B per pair and 48 B per drop, per projection.
+    # DRAM / L2 bytes, instructions per query and issue utilisation: committed ncu captures of the same build.
     ncu = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            ncu = json.load(open(tpath)).get("k_project", {})
+            ncu = json.load(open(tpath))
         except Exception:
             ncu = {}
     iters = int(st["iters"])
+    ms_loop = float(np.mean(reg_ms))
+    alg_loop = iters * alg_bytes
     each = np.mean(np.stack([e for e in proj_each if e.shape[0] == iters]), axis=0) if any(e.shape[0] == iters for e in proj_each) else np.zeros(0)
     miss = proj_miss[-1] if proj_miss else np.zeros(0, np.int32)
-    regimes = {}
-    for name, sel in (("tree_walk", miss < 0), ("tiles", miss >= 0)):
-        if each.shape[0] == miss.shape[0] and sel.any():
-            ms = float(each[sel].mean())
-            regimes[name] = {"launches_per_step": int(sel.sum()), "ms_per_launch": ms, "achieved_gbs": alg_bytes / (ms * 1e-3) / 1e9,
-                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, **ncu.get(name, {})}
-            if name == "tiles":
-                regimes[name]["queries_sent_to_the_tree_per_launch"] = float(miss[sel].mean())
-    traffic = None
-    if regimes and all("dram_bytes_per_launch" in r for r in regimes.values()):
-        traffic = int(sum(r["dram_bytes_per_launch"] * r["launches_per_step"] for r in regimes.values()) / sum(r["launches_per_step"] for r in regimes.values()))
-    share = ms_proj * float(np.mean(proj_n)) / (total_ms / args.steps) if world == 1 else None
-    roofline = {"bound": "hbm", "kernel": "k_project (knn + IMLS projection; tree walk in the first projections, candidate tiles once the pose settles)",
-                "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_proj,
-                "launches_per_step": float(np.mean(proj_n)), "share_of_step": share,
-                "timing": "CUDA events around every k_project launch, same steps repeated right after the timed region",
-                "regimes": regimes,
-                "note": "tree walk: the 1 M-pt map (32 MB sorted) is L2-resident, DRAM traffic is far below algorithmic bytes and the "
-                        "kernel is issue- / latency-bound (inst_per_query, issue_active_pct); tiles: 1 KB per query streams from HBM"}
+    phases = {}
+    if each.shape[0] == miss.shape[0] and each.shape[0] > 0:
+        for name, sel in (("tree_walk", miss < 0), ("tiles", miss >= 0)):
+            if sel.any():
+                ms = float(each[sel].mean())
+                phases[name] = {"projections_per_launch": int(sel.sum()), "ms_per_projection": ms, "achieved_gbs": alg_bytes / (ms * 1e-3) / 1e9,
+                                **ncu.get("k_project", {}).get(name, {})}
+        if "tiles" in phases:
+            phases["tiles"]["queries_sent_to_the_tree_per_projection"] = float(miss[miss >= 0].mean())
+        phases["reduce_solve_barriers_ms_per_launch"] = ms_loop - float(each.sum())
+    kl = ncu.get("k_register_loop", {})
+    achieved = alg_loop / (ms_loop * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_register_loop (the whole ICP loop in one cooperative launch: per iteration k-NN + IMLS projection -- tree "
+                                          "walk first, candidate tiles once the pose settles -- normal-equation reduce, 6x6 solve, pose update)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": kl.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_loop), "ms_per_launch": ms_loop, "launches_per_step": 1.0,
+                "share_of_step": (ms_loop / (total_ms / args.steps)) if world == 1 else None,
+                "timing": "CUDA events around the launch inside the timed steps (plo_last_timings); phases: the same steps repeated in the "
+                          "enqueue-all mode with an event pair around every projection",
+                "l2_bytes_per_launch": kl.get("l2_bytes_per_launch"), "inst_per_query": kl.get("inst_per_query"),
+                "issue_active_pct": kl.get("issue_active_pct"), "l2_hit_pct": kl.get("l2_hit_pct"),
+                "phases": phases,
+                "note": "not HBM-bound and not meant to be at this size: the 1 M-pt map (32 MB sorted) stays in the 126 MB L2, the tree walk is "
+                        "issue- / latency-bound (inst_per_query, issue_active_pct), L2 traffic is ~26x the algorithmic bytes; only the tile "
+                        "projections stream from HBM (1 KB per query)"}
 
     # ---- CPU baseline (oracle port, all host threads), same bytes, same process ----------
     cpu = None

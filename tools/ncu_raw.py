@@ -5,7 +5,7 @@ import csv, json, sys
 
 KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum", "launch__registers_per_thread",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 STALL = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio"
@@ -35,7 +35,7 @@ if sys.argv[1] == "--json":
         inst = val(d, u, "smsp__inst_executed.sum")
         issue = val(d, u, "smsp__issue_active.avg.pct_of_peak_sustained_active") or val(d, u, "smsp__issue_active.avg.pct")
         out[name] = {"dram_bytes_per_launch": int(val(d, u, "dram__bytes_read.sum") + val(d, u, "dram__bytes_write.sum")),
-                     "l2_bytes_per_launch": int(val(d, u, "lts__t_bytes.sum")), "inst_per_query": round(inst / nq, 1),
+                     "l2_bytes_per_launch": int(32 * val(d, u, "lts__t_sectors.sum")), "inst_per_query": round(inst / nq, 1),
                      "issue_active_pct": None if issue is None else round(issue, 1),
                      "l1_hit_pct": round(val(d, u, "l1tex__t_sector_hit_rate.pct"), 1), "l2_hit_pct": round(val(d, u, "lts__t_sector_hit_rate.pct"), 1),
                      "warps_active_pct": round(val(d, u, "sm__warps_active.avg.pct_of_peak_sustained_active"), 1),
@@ -57,7 +57,7 @@ if sys.argv[1] == "--kernels":
             us = val(d, units, "gpu__time_duration.sum")
             dr = (val(d, units, "dram__bytes_read.sum") or 0) + (val(d, units, "dram__bytes_write.sum") or 0)
             a = agg.setdefault(name, [0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, d.get("launch__registers_per_thread", ""), d.get("launch__grid_size", "")])
-            a[0] += 1; a[1] += us; a[2] += dr; a[3] += val(d, units, "lts__t_bytes.sum") or 0
+            a[0] += 1; a[1] += us; a[2] += dr; a[3] += 32 * (val(d, units, "lts__t_sectors.sum") or 0)
             a[4] += val(d, units, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0
             a[5] += val(d, units, "sm__warps_active.avg.pct_of_peak_sustained_active") or 0
             a[6] += val(d, units, "lts__t_sector_hit_rate.pct") or 0
