@@ -868,6 +868,43 @@ def test_pca_normals_full_cfg1_pair(oracle_mod):
     assert (herr[~tight] <= hbar[~tight] + 3.0 * 4 * touched[ok][~tight]).all()
 
 
+def test_resident_loop_fuzz_sizes_and_long_runs(oracle_mod):
+    """k_register_loop (one cooperative launch per registration) over cloud sizes from a handful of points to tens of
+    thousands -- one block to the full grid, every group size of the tile path -- and over registrations forced to run all
+    30 iterations (convergence thresholds at zero: the tile path answers ~27 projections in a row, misses and refreshes
+    included): status, iterations, pairs, drop counters and pose against the oracle; the second run of the same context
+    and the graph / enqueue-all forms of the loop give bitwise the same pose."""
+    rng = np.random.default_rng(4242)
+    base = W.hdl64_pair(max_source=40000, max_target=60000)
+    cases = [(7, 300), (33, 2000), (500, 2000), (2000, 20000), (9000, 60000), (40000, 60000)]
+    for n_s, n_t in cases:
+        src = base.source[np.sort(rng.choice(base.source.shape[0], n_s, replace=False))]
+        tgt = base.target[np.sort(rng.choice(base.target.shape[0], n_t, replace=False))]
+        for kw in (dict(), dict(delta_dist_threshold=0.0, delta_angle_threshold=0.0)):
+            ctx, orc = _both(oracle_mod, tgt, src, **kw)
+            Tg, sg = ctx.register()
+            To, so = orc.register()
+            assert sg["status"] == so["status"] and sg["iters"] == so["iters"] and sg["pairs"] == so["pairs"], (n_s, n_t, kw, sg, so)
+            assert np.array_equal(sg["counters"], so["counters"]), (n_s, n_t, kw)
+            if so["pairs"] >= 6:
+                assert _rot_err(Tg[:3, :3], To[:3, :3]) < POSE_RAD and np.linalg.norm(Tg[:3, 3] - To[:3, 3]) < POSE_M, (n_s, n_t, kw)
+            if kw:
+                assert sg["iters"] == 30 or sg["status"] == 3
+                if sg["iters"] == 30 and n_s >= 500:
+                    assert (ctx.last_tile_misses()[3:] >= 0).all()          # the tile path was in use
+            T2, s2 = ctx.register()                                         # same clouds: starts from tiles and temporal bounds
+            assert np.array_equal(Tg, T2) and s2["iters"] == sg["iters"]
+            for knob in ("loop_kernel", "no_graph"):
+                c2 = plo.Context(0, plo.default_params(**kw))
+                c2.set_tuning(knob, 0 if knob == "loop_kernel" else 1)
+                c2.set_target(tgt)
+                c2.set_source(src)
+                T3, s3 = c2.register()
+                assert np.array_equal(Tg, T3) and s3["iters"] == sg["iters"], (n_s, n_t, kw, knob)
+                c2.close()
+            ctx.close()
+
+
 def test_device_inputs_produced_on_another_stream(oracle_mod):
     """torch CUDA tensors are passed by pointer and read on the context's own stream: the Context orders that stream
     behind the torch stream that produced them (an event, no global synchronisation).  The clouds are produced on a
