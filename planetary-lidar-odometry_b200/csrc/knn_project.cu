@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_project(const
   ps.use_prev = st->use_prev;
   ps.store = st->warm != 0;
   ps.tiles = ps.use_prev && st->tiles_ready;
-  ps.chunk = chunk_arg > 0 ? chunk_arg : st->chunk;
+  ps.chunk = chunk_arg > 0 ? chunk_arg : (chunk_arg < 0 ? min(st->chunk, -chunk_arg) : st->chunk);   // > 0: forced, < 0: cap
   const int n_src = counts->n_source;
   const int n_tgt = m.n_raw > 0 ? counts->n_target : 0;
   // rPose rows (src/laser_odometry.cpp:530-535), kept in shared memory: 24 registers less per thread
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_register_loop
     ps.use_prev = s_st.use_prev;
     ps.store = s_st.warm != 0;
     ps.tiles = ps.use_prev && s_st.tiles_ready;
-    ps.chunk = chunk_arg > 0 ? chunk_arg : s_st.chunk;
+    ps.chunk = chunk_arg > 0 ? chunk_arg : (chunk_arg < 0 ? min(s_st.chunk, -chunk_arg) : s_st.chunk);
     if (threadIdx.x < 12) T[threadIdx.x] = s_st.rPose[threadIdx.x];
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
@@ -979,8 +979,12 @@ void fill_project_launch(plo_ctx* c, ProjectLaunch& a) {
   // an atomic counter.  The chunk length comes from the device-side loop state (see finish_iteration)
   // unless the cloud is too small to fill the GPU (then 1) or the tuning knob overrides it.
   const int64_t slots = (int64_t)plo_grid(c, PLO_MINB) * kWarpsPerBlock;
-  a.chunk = (c->m_raw < 16 * slots) ? 1 : 0;
-  if (c->tune_chunk >= 0) a.chunk = c->tune_chunk;   // tuning knob (0 = device-side policy)
+  // the device-side policy (8 / 4 / 1) is capped so that every warp of the grid gets at least ~2.5 chunks: chunks of
+  // consecutive points buy the carry bound (no greedy descent per query), too few of them unbalance the grid
+  int cap = 8;
+  while (cap > 1 && c->m_raw * 2 < (int64_t)cap * 5 * slots) cap >>= 1;
+  a.chunk = -cap;
+  if (c->tune_chunk >= 0) a.chunk = c->tune_chunk;   // tuning knob: > 0 forces a length, 0 = device-side policy uncapped
   // settled path: a warp takes `group` consecutive queries at a time (their per-query scalars one per lane); small
   // clouds get small groups so that every warp of the grid has work (a 2 000-point source in groups of 32 would keep
   // 63 warps busy, each answering 32 queries one after the other)
