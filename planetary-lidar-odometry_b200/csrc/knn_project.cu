@@ -707,10 +707,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PLO_MINB) k_register_loop
     stamp(dbg_it, 4);
     sum_block_partials(partials, (int)gridDim.x, s_sum, s_red);
     stamp(dbg_it, 5);
-    if (threadIdx.x == 0) {
-      if (ps.store) s_st.tiles_ready = 1;
-      solve_from_sums(s_sum, &s_st, P, 1, (cudaGraphConditionalHandle)0, 0, 0);
-    }
+    if (threadIdx.x == 0 && ps.store) s_st.tiles_ready = 1;
+    if (threadIdx.x < 32) solve_from_sums(s_sum, &s_st, P, 1, (cudaGraphConditionalHandle)0, 0, 0);   // warp 0, collectively
     __syncthreads();
     stamp(dbg_it, 6);
   }
@@ -1085,3 +1083,9 @@ int plo_launch_register_loop(plo_ctx* c) {
   c->launches++;
   return PLO_OK;
 }
+
+#ifdef PLO_LOOP_TIMING
+extern "C" __attribute__((visibility("default"))) int plo_debug_solve_stamps(unsigned long long* out8) {
+  return (int)cudaMemcpyFromSymbol(out8, g_solve_stamp, sizeof(unsigned long long) * 8);
+}
+#endif

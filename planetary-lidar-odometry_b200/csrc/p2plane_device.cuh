@@ -11,6 +11,13 @@
 
 namespace {
 
+#ifdef PLO_LOOP_TIMING
+static __device__ unsigned long long g_solve_stamp[8];
+#define PLO_SOLVE_STAMP(i) do { if (blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_solve_stamp[i] = t_; } } while (0)
+#else
+#define PLO_SOLVE_STAMP(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void ab_row(const double s[3], const double d[3], const double n[3], double a[6], double& b) {
   // src/solver.cpp:185-192
   a[0] = __dsub_rn(__dmul_rn(n[2], s[1]), __dmul_rn(n[1], s[2]));
@@ -61,15 +68,19 @@ __device__ __forceinline__ void accumulate_pair(double acc[PLO_NSUM], const doub
   acc[28] += w * b * b;
 }
 
-// ---- 6x6 solve + pose update (one thread) -------------------------------------------
+// ---- 6x6 solve + pose update (one warp) ---------------------------------------------
 
 __device__ void rodrigues(const double r[3], double R[9]) {
   // Eigen AngleAxisd(rot.norm(), rot.normalized()).toRotationMatrix(); a zero vector stays zero
   const double z = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
   const double angle = sqrt(z);
   double ax[3] = {r[0], r[1], r[2]};
-  if (z > 0.0) { ax[0] /= angle; ax[1] /= angle; ax[2] /= angle; }
-  const double sn = sin(angle), cs = cos(angle);
+  if (z > 0.0) {
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) ax[i] /= angle;
+  }
+  double sn, cs;
+  sincos(angle, &sn, &cs);
   const double sa[3] = {sn * ax[0], sn * ax[1], sn * ax[2]};
   const double ca[3] = {(1.0 - cs) * ax[0], (1.0 - cs) * ax[1], (1.0 - cs) * ax[2]};
   double tmp;
@@ -82,6 +93,7 @@ __device__ void rodrigues(const double r[3], double R[9]) {
 // orthogonal polar factor of a near-rotation (== U V^T of its SVD, src/solver.cpp:207-213):
 // Newton iteration X <- (X + X^-T) / 2, quadratically convergent
 __device__ void polar_orthogonalize(double R[9]) {
+#pragma unroll 1
   for (int it = 0; it < 4; ++it) {
     const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
     const double c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
@@ -95,57 +107,6 @@ __device__ void polar_orthogonalize(double R[9]) {
   }
 }
 
-// diagonally pivoted LDL^T solve of H x = g; returns the number of pivots used.
-// A pivot is dropped when the remaining diagonal is below (max|H_jj| * eps^2) * (cnt-k)/cnt,
-// the squared form of Eigen's ColPivHouseholderQR threshold_helper test (H_jj = |col j|^2).
-// x must NOT live on the caller's stack: inlined into k_solve_update, nvcc 12.9 let a local x[] share a stack slot
-// with A[][] (wrong results); the callers pass a shared-memory array.
-__device__ __forceinline__ int solve_ldlt6(const double H21[21], const double g[6], double count, double x[6]) {
-  double A[6][6];
-  int t = 0;
-  for (int p = 0; p < 6; ++p)
-    for (int q = p; q < 6; ++q) { A[p][q] = H21[t]; A[q][p] = H21[t]; ++t; }
-  int perm[6] = {0, 1, 2, 3, 4, 5};
-  double rhs[6];
-  for (int i = 0; i < 6; ++i) rhs[i] = g[i];
-  double hmax = 0.0;
-  for (int i = 0; i < 6; ++i) hmax = fmax(hmax, A[i][i]);
-  const double helper = (hmax * DBL_EPSILON) * DBL_EPSILON / fmax(count, 1.0);
-  int rank = 6;
-  for (int k = 0; k < 6; ++k) {
-    int piv = k;
-    for (int j = k + 1; j < 6; ++j) if (A[j][j] > A[piv][piv]) piv = j;
-    const double dk = A[piv][piv];
-    if (!(dk > 0.0) || dk < helper * (count - k)) { rank = k; break; }
-    if (piv != k) {
-      for (int j = 0; j < 6; ++j) { const double tmp = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = tmp; }
-      for (int j = 0; j < 6; ++j) { const double tmp = A[j][k]; A[j][k] = A[j][piv]; A[j][piv] = tmp; }
-      const double tr = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = tr;
-      const int tp = perm[k]; perm[k] = perm[piv]; perm[piv] = tp;
-    }
-    for (int i = k + 1; i < 6; ++i) {
-      const double lik = A[k][i] / dk;   // row k stays unscaled (A[k][i] == a_ik), column k becomes L
-      for (int j = k + 1; j <= i; ++j) { A[i][j] -= lik * A[k][j]; A[j][i] = A[i][j]; }
-      A[i][k] = lik;
-    }
-  }
-  for (int i = 0; i < 6; ++i) x[i] = 0.0;
-  double y[6];
-  for (int i = 0; i < rank; ++i) {          // L z = rhs
-    double sacc = rhs[i];
-    for (int j = 0; j < i; ++j) sacc -= A[i][j] * y[j];
-    y[i] = sacc;
-  }
-  for (int i = 0; i < rank; ++i) y[i] /= A[i][i];   // D
-  for (int i = rank - 1; i >= 0; --i) {     // L^T x = y
-    double sacc = y[i];
-    for (int j = i + 1; j < rank; ++j) sacc -= A[j][i] * y[j];
-    y[i] = sacc;
-  }
-  for (int i = 0; i < rank; ++i) x[perm[i]] = y[i];
-  return rank;
-}
-
 // x -> deltaTrans (src/solver.cpp:203-217): Rodrigues, orthogonal polar factor, translation
 __device__ void delta_from_x(const double x[6], double D[16]) {
   double R[9];
@@ -155,89 +116,211 @@ __device__ void delta_from_x(const double x[6], double D[16]) {
   for (int i = 0; i < 16; ++i) D[i] = Dl[i];
 }
 
-// tail of one loop iteration (one thread): delta, rPose = delta * rPose (src/laser_odometry.cpp:619),
-// convergence test (:628-646), loop condition of the resident graph
-__device__ void finish_iteration(DevState* __restrict__ st, const DevParams& P, const double x[6], int rank, int advance_loop,
-                                 cudaGraphConditionalHandle cond, int use_cond) {
-  st->rank = rank;
-  double D[16];
-  delta_from_x(x, D);
-  for (int i = 0; i < 16; ++i) st->delta[i] = D[i];
-  const double dd = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);   // :628-632
-  double ct = ((D[0] + D[5] + D[10]) - 1.0) / 2.0;                   // :636-638
-  ct = fmin(1.0, fmax(ct, -1.0));
-  const double da = acos(ct);
-  st->delta_dist = dd;
-  st->delta_angle = da;
-  if (!advance_loop) return;
-  double nP[16];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      double sacc = 0.0;
-      for (int k = 0; k < 4; ++k) sacc += D[i * 4 + k] * st->rPose[k * 4 + j];
-      nP[i * 4 + j] = sacc;
+// Diagonally pivoted LDL^T solve of H x = g, warp-collective (all 32 lanes of one warp call it); returns the number of
+// pivots used.  A pivot is dropped when the remaining diagonal is below (max|H_jj| * eps^2) * (cnt-k)/cnt, the squared form
+// of Eigen's ColPivHouseholderQR threshold_helper test (H_jj = |col j|^2).  The 6 x 7 augmented matrix [H | g] lives in shared
+// memory, one or two elements per lane (element e = row e / 7, column e % 7; a lane owns e = lane and e = lane + 32), so a pivot step is
+// a scan of the six diagonal entries, two shared-memory reads per element, one division in parallel on every lane and
+// one multiply-subtract.  The solve runs once per ICP iteration on code the projection has evicted from the
+// instruction cache, so what it costs is its SIZE (a one-thread version over a local 6 x 6 array: 8 us of 15, measured
+// with PLO_LOOP_TIMING; this one 2-3) -- the loops below are deliberately not unrolled.  Both copies of a symmetric pair
+// are updated with the same expression, so the matrix stays exactly symmetric.
+// H21: 21 packed upper entries, g6: right-hand side (any address space), both times `scale`; x: 6 doubles, shared memory.
+__device__ __forceinline__ int solve_ldlt6_warp(const double* H21, const double* g6, double scale, double count, double* x) {
+  __shared__ double s_buf[2][42];   // [6][7] row-major, column 6 = right-hand side; a pivot step reads one copy, writes the other
+  const int lane = threadIdx.x & 31;
+  double* M = s_buf[0];
+  double* N = s_buf[1];
+  // this lane's two elements: (i0, j0) = element lane, (i1, j1) = element lane + 32 (lanes 0-9 only)
+  const bool two = lane < 10;
+  const int e1 = two ? lane + 32 : 41;
+  const int i0 = lane / 7, j0 = lane % 7, i1 = e1 / 7, j1 = e1 % 7;
+  {
+    const int a0 = min(i0, j0), b0 = max(i0, j0), a1 = min(i1, j1), b1 = max(i1, j1);
+    M[lane] = (j0 == 6 ? g6[i0] : H21[a0 * 6 - a0 * (a0 - 1) / 2 + (b0 - a0)]) * scale;
+    if (two) M[lane + 32] = (j1 == 6 ? g6[i1] : H21[a1 * 6 - a1 * (a1 - 1) / 2 + (b1 - a1)]) * scale;
+  }
+  if (lane < 6) x[lane] = 0.0;
+  // row p is read at [hi] and [lo]: M[i][j] -= (M[p][hi] / dp) * M[p][lo], the same expression for (i, j) and (j, i)
+  // (M[i][p] == M[p][i] by symmetry), so the matrix stays exactly symmetric
+  const int hi0 = j0 == 6 ? i0 : max(i0, j0), lo0 = j0 == 6 ? 6 : min(i0, j0);
+  const int hi1 = j1 == 6 ? i1 : max(i1, j1), lo1 = j1 == 6 ? 6 : min(i1, j1);
+  __syncwarp();
+  double dg[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dg[i] = M[i * 8];
+  double hmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) hmax = fmax(hmax, dg[i]);
+  const double helper = (hmax * DBL_EPSILON) * DBL_EPSILON / fmax(count, 1.0);
+  unsigned done = 0u, order = 0u;   // pivots taken (bit per index), their order (3 bits per step)
+  int rank = 0;
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    // largest remaining diagonal entry, smallest index on exact ties; every lane finds the same one
+    int p = -1;
+    double dp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double v = M[i * 8];
+      if (!((done >> i) & 1u) && (p < 0 || v > dp)) { p = i; dp = v; }
     }
-  for (int i = 0; i < 16; ++i) st->rPose[i] = nP[i];   // :619
-  st->iters += 1;
-  st->use_prev = 1;   // the projection just consumed left its k-th distances behind
-  // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
-  // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
-  st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
-  st->warm = (dd < 0.05 && da < 0.01) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
-  if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
-  else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
-  if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
+    if (!(dp > 0.0) || dp < helper * (count - k)) break;
+    done |= 1u << p;
+    order |= (unsigned)p << (3 * k);
+    rank = k + 1;
+    // rows and columns not yet taken (the right-hand side column always)
+    const double m0 = M[lane], m1 = M[e1];
+    const double a0 = M[p * 7 + hi0], b0 = M[p * 7 + lo0], a1 = M[p * 7 + hi1], b1 = M[p * 7 + lo1];
+    const bool live0 = !((done >> i0) & 1u) && (j0 == 6 || !((done >> j0) & 1u));
+    const bool live1 = !((done >> i1) & 1u) && (j1 == 6 || !((done >> j1) & 1u));
+    N[lane] = live0 ? m0 - (a0 / dp) * b0 : m0;
+    if (two) N[lane + 32] = live1 ? m1 - (a1 / dp) * b1 : m1;
+    __syncwarp();
+    double* t = M; M = N; N = t;
+  }
+  // back substitution in reverse pivot order, column by column: x[p] = rhs[p] / M[p][p], then rhs[i] -= M[i][p] x[p] on the
+  // lanes (i < 6) of the pivots still to come
+  double rhs = lane < 6 ? M[lane * 7 + 6] : 0.0;
+#pragma unroll 1
+  for (int k = rank - 1; k >= 0; --k) {
+    const int p = (order >> (3 * k)) & 7;
+    const double xp = __shfl_sync(PLO_FULL_MASK, rhs, p) / M[p * 8];
+    if (lane == p) x[p] = xp;
+    if (lane < 6) rhs -= M[lane * 7 + p] * xp;
+  }
+  __syncwarp();
+  return rank;
 }
 
-// One thread: the reduced sums (PLO_NSUM values: 21 H, 6 g, sum w, sum w b^2, pair count, six drop counters) -> loop
-// state, 6x6 solve, pose update.  stage 0: weighted LS (one pass).  Trimmed LS (src/solver.cpp:74-166): stage 1 =
-// first solve on all pairs, only x0 is kept (:107); stage 2 = second solve on the pairs selected by residual rank
-// (:137) + loop tail.  DRPM (:499-603): stage 3 = the sums only; k_drpm_eigen / k_drpm_noise / k_drpm_finish go on.
+// tail of one loop iteration, warp-collective: delta, rPose = delta * rPose (src/laser_odometry.cpp:619), convergence
+// test (:628-646), loop condition of the resident graph.  x: shared memory.  The polar factor and the 4 x 4 product are
+// spread over lanes (one matrix element each) for the same reason as the solve: fewer instructions to fetch.
+__device__ __forceinline__ void finish_iteration(DevState* __restrict__ st, const DevParams& P, const double* x, int rank, int advance_loop,
+                                                 cudaGraphConditionalHandle cond, int use_cond) {
+  const int lane = threadIdx.x & 31;
+  __shared__ double s_D[16];
+  PLO_SOLVE_STAMP(3);
+  if (lane == 0) {
+    st->rank = rank;
+    double R[9];
+    rodrigues(x, R);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) s_D[i * 4 + j] = R[i * 3 + j];
+      s_D[i * 4 + 3] = x[3 + i];
+      s_D[12 + i] = 0.0;
+    }
+    s_D[15] = 1.0;
+  }
+  __syncwarp();
+  {   // polar_orthogonalize(), element (i, j) on lane 3 i + j: same expressions, same bits
+    const int e = lane < 9 ? lane : 0, i = e / 3, j = e % 3;
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+      const double c = s_D[i1 * 4 + j1] * s_D[i2 * 4 + j2] - s_D[i1 * 4 + j2] * s_D[i2 * 4 + j1];
+      const double det = s_D[0] * __shfl_sync(PLO_FULL_MASK, c, 0) + s_D[1] * __shfl_sync(PLO_FULL_MASK, c, 1) +
+                         s_D[2] * __shfl_sync(PLO_FULL_MASK, c, 2);
+      if (!(fabs(det) > 1e-300)) break;
+      const double r = 0.5 * (s_D[i * 4 + j] + c * (1.0 / det));
+      __syncwarp();
+      if (lane < 9) s_D[i * 4 + j] = r;
+      __syncwarp();
+    }
+  }
+  PLO_SOLVE_STAMP(4);
+  if (lane < 16) st->delta[lane] = s_D[lane];
+  double dd = 0.0, da = 0.0;
+  if (lane == 0) {
+    dd = sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5]);          // :628-632
+    double ct = ((s_D[0] + s_D[5] + s_D[10]) - 1.0) / 2.0;       // :636-638
+    ct = fmin(1.0, fmax(ct, -1.0));
+    da = acos(ct);
+    st->delta_dist = dd;
+    st->delta_angle = da;
+  }
+  if (!advance_loop) { __syncwarp(); return; }
+  double np = 0.0;
+  if (lane < 16) {
+    const int i = lane >> 2, j = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) np += s_D[i * 4 + k] * st->rPose[k * 4 + j];
+  }
+  __syncwarp();
+  if (lane < 16) st->rPose[lane] = np;   // :619
+  if (lane == 0) {
+    st->iters += 1;
+    st->use_prev = 1;   // the projection just consumed left its k-th distances behind
+    // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
+    // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
+    st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
+    st->warm = (dd < 0.05 && da < 0.01) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
+    if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
+    else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
+    if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?
+  }
+  __syncwarp();
+  PLO_SOLVE_STAMP(5);
+}
+
+// One WARP (all 32 lanes call it; lane 0 does the scalar work): the reduced sums (PLO_NSUM values: 21 H, 6 g, sum w,
+// sum w b^2, pair count, six drop counters) -> loop state, 6x6 solve, pose update.  stage 0: weighted LS (one pass).
+// Trimmed LS (src/solver.cpp:74-166): stage 1 = first solve on all pairs, only x0 is kept (:107); stage 2 = second solve on
+// the pairs selected by residual rank (:137) + loop tail.  DRPM (:499-603): stage 3 = the sums only; k_drpm_eigen /
+// k_drpm_noise / k_drpm_finish go on.  s_sum and x live in shared memory.
 __device__ __noinline__ void solve_from_sums(const double* s_sum, DevState* __restrict__ st, const DevParams& P, int advance_loop,
-                                cudaGraphConditionalHandle cond, int use_cond, int stage) {
+                                             cudaGraphConditionalHandle cond, int use_cond, int stage) {
+  const int lane = threadIdx.x & 31;
+  PLO_SOLVE_STAMP(0);
   const double count = s_sum[29];
-  double sw = s_sum[27];
-  for (int i = 0; i < 21; ++i) st->H[i] = s_sum[i];
-  for (int i = 0; i < 6; ++i) st->g[i] = s_sum[21 + i];
-  st->sw = sw;
-  st->swbb = s_sum[28];
-  if (stage != 2) {   // the statistics describe the projection, not the trimmed subset
-    st->pairs = (long long)count;
-    for (int i = 0; i < 6; ++i) st->dropped[i] = (long long)s_sum[30 + i];
-    st->rms = count > 0.0 ? sqrt(s_sum[28] / fmax(sw, 1e-300)) : 0.0;
+  const double sw = s_sum[27];
+  if (lane < 21) st->H[lane] = s_sum[lane];
+  if (lane < 6) st->g[lane] = s_sum[21 + lane];
+  if (lane == 0) {
+    st->sw = sw;
+    st->swbb = s_sum[28];
+    if (stage != 2) {   // the statistics describe the projection, not the trimmed subset
+      st->pairs = (long long)count;
+      for (int i = 0; i < 6; ++i) st->dropped[i] = (long long)s_sum[30 + i];
+      st->rms = count > 0.0 ? sqrt(s_sum[28] / fmax(sw, 1e-300)) : 0.0;
+    }
   }
   if (advance_loop && count < (double)P.correspond_number) {   // src/laser_odometry.cpp:570-576
-    st->status = PLO_REG_TOO_FEW_PAIRS;
-    st->done = 1;
-    if (use_cond) cudaGraphSetConditional(cond, 0);
+    if (lane == 0) {
+      st->status = PLO_REG_TOO_FEW_PAIRS;
+      st->done = 1;
+      if (use_cond) cudaGraphSetConditional(cond, 0);
+    }
+    __syncwarp();
     return;
   }
-  double H[21], g[6];
   // weights are normalised to sum 1 in the reference (src/solver.cpp:361-364); same argmin
   const double scale = (!P.ext_weights && P.weight_mode == PLO_W_HUBER_EXP && sw > 0.0) ? 1.0 / sw : 1.0;
-  bool finite = true;
-  for (int i = 0; i < 21; ++i) { H[i] = s_sum[i] * scale; finite = finite && isfinite(H[i]); }
-  for (int i = 0; i < 6; ++i) { g[i] = s_sum[21 + i] * scale; finite = finite && isfinite(g[i]); }
-  if (stage == 3) return;
-  __shared__ double x[6];   // see solve_ldlt6
-  const int rank = solve_ldlt6(H, g, stage == 2 ? sw : count, x);
+  bool finite = (lane < 27) ? isfinite(s_sum[lane] * scale) : true;
+  finite = __all_sync(PLO_FULL_MASK, finite);
+  if (stage == 3) { __syncwarp(); return; }
+  __shared__ double x[6];
+  PLO_SOLVE_STAMP(1);
+  const int rank = solve_ldlt6_warp(s_sum, s_sum + 21, scale, stage == 2 ? sw : count, x);
+  PLO_SOLVE_STAMP(2);
   if (advance_loop && stage != 1 && (rank == 0 || !finite)) {
     // no pivot at all (every pair had a zero row) or non-finite sums: the reference would carry NaN / a zero step
     // through its remaining iterations (src/laser_odometry.cpp:611-616 only breaks on `false`, which WeightedLS never
     // returns); here the loop ends with the pose of the previous iteration and says so
-    st->rank = rank;
-    st->status = PLO_REG_SOLVE_FAILED;
-    st->done = 1;
-    if (use_cond) cudaGraphSetConditional(cond, 0);
-    return;
+    if (lane == 0) {
+      st->rank = rank;
+      st->status = PLO_REG_SOLVE_FAILED;
+      st->done = 1;
+      if (use_cond) cudaGraphSetConditional(cond, 0);
+    }
+  } else if (stage == 1) {
+    if (lane == 0) st->rank = rank;
+    if (lane < 6) st->x0[lane] = x[lane];   // the loop condition keeps its value (1): the body goes on with the selection
+  } else {
+    if (lane < 6) st->probs[lane] = 0.0;
+    finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
   }
-  if (stage == 1) {
-    st->rank = rank;
-    for (int i = 0; i < 6; ++i) st->x0[i] = x[i];
-    return;   // the loop condition keeps its value (1): the body goes on with the selection
-  }
-  for (int i = 0; i < 6; ++i) st->probs[i] = 0.0;
-  finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
+  __syncwarp();
 }
 
 // ---- block-level reduction of the normal equations, shared by k_reduce_solve and k_register_loop ------------------

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kFusedReduceWarps * 32) k_reduce_solve(const f
   if (threadIdx.x == 0) *done_ticket = 0;
   __shared__ double s_sum[PLO_NSUM];
   sum_block_partials(partials, (int)gridDim.x, s_sum, s_red);
-  if (threadIdx.x == 0) solve_from_sums(s_sum, st, P, 1, cond, use_cond, 0);
+  if (threadIdx.x < 32) solve_from_sums(s_sum, st, P, 1, cond, use_cond, 0);   // warp 0, collectively
 }
 
 // reference-shaped inputs (n x 3 doubles each, optional weights) -> per-block partial sums
@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(256) k_solve_update(const double* __restrict__
   __shared__ double s_sum[PLO_NSUM];
   __shared__ double s_stage[8][PLO_NSUM];
   sum_block_partials(partials, n_partials, s_sum, s_stage);
-  if (threadIdx.x != 0) return;
-  solve_from_sums(s_sum, st, P, advance_loop, cond, use_cond, stage);
+  if (threadIdx.x >= 32) return;
+  solve_from_sums(s_sum, st, P, advance_loop, cond, use_cond, stage);   // warp 0, collectively
 }
 
 // ---- RANSAC front (src/solver.cpp:238-326) on the compacted pairs, one block --------------------
@@ -574,52 +574,56 @@ __global__ void __launch_bounds__(64) k_drpm_finish(const double* __restrict__ p
     s_sum[threadIdx.x] = v;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x >= 32) return;   // warp 0: lane 0 for the probabilities, all lanes for the solve and the loop tail
   const double sw = st->sw;
   const double scale = P.ext_weights ? 1.0 : (sw > 0.0 ? 1.0 / sw : 1.0);
-  double H[21], g[6], Hf[36];
-  for (int i = 0; i < 21; ++i) H[i] = st->H[i] * scale;
-  for (int i = 0; i < 6; ++i) g[i] = st->g[i] * scale;
-  int t = 0;
-  for (int a = 0; a < 6; ++a)
-    for (int b = a; b < 6; ++b) { Hf[a * 6 + b] = H[t]; Hf[b * 6 + a] = H[t]; ++t; }
-  double probs[6], minp = CUDART_INF;
-  for (int k = 0; k < 6; ++k) {
-    double meas = 0.0, noise = 0.0;
-    for (int r = 0; r < 6; ++r) {
-      double t1 = 0.0, t2 = 0.0;
-      for (int c = 0; c < 6; ++c) { t1 += Hf[r * 6 + c] * st->U[c * 6 + k]; t2 += s_sum[r * 6 + c] * st->U[c * 6 + k]; }
-      meas += st->U[r * 6 + k] * t1;
-      noise += st->U[r * 6 + k] * t2;
+  __shared__ double x[6];
+  __shared__ int s_weighted;
+  if (threadIdx.x == 0) {
+    double H[21], g[6], Hf[36];
+    for (int i = 0; i < 21; ++i) H[i] = st->H[i] * scale;
+    for (int i = 0; i < 6; ++i) g[i] = st->g[i] * scale;
+    int t = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) { Hf[a * 6 + b] = H[t]; Hf[b * 6 + a] = H[t]; ++t; }
+    double probs[6], minp = CUDART_INF;
+    for (int k = 0; k < 6; ++k) {
+      double meas = 0.0, noise = 0.0;
+      for (int r = 0; r < 6; ++r) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int c = 0; c < 6; ++c) { t1 += Hf[r * 6 + c] * st->U[c * 6 + k]; t2 += s_sum[r * 6 + c] * st->U[c * 6 + k]; }
+        meas += st->U[r * 6 + k] * t1;
+        noise += st->U[r * 6 + k] * t2;
+      }
+      const double sd = sqrt(s_sum[36 + k]);
+      const double test_point = meas / (1.0 + 10.0);   // snr_factor = 10, src/solver.cpp:547
+      double pr;
+      if (!(noise == noise) || !(sd == sd) || !(test_point == test_point)) pr = 0.0;
+      else if (!(sd > 0.0)) pr = test_point >= noise ? 1.0 : 0.0;
+      else pr = 0.5 * erfc(-(test_point - noise) / (sd * sqrt(2.0)));   // boost normal cdf
+      probs[k] = pr;
+      st->probs[k] = pr;
+      if (pr < minp) minp = pr;
     }
-    const double sd = sqrt(s_sum[36 + k]);
-    const double test_point = meas / (1.0 + 10.0);   // snr_factor = 10, src/solver.cpp:547
-    double pr;
-    if (!(noise == noise) || !(sd == sd) || !(test_point == test_point)) pr = 0.0;
-    else if (!(sd > 0.0)) pr = test_point >= noise ? 1.0 : 0.0;
-    else pr = 0.5 * erfc(-(test_point - noise) / (sd * sqrt(2.0)));   // boost normal cdf
-    probs[k] = pr;
-    st->probs[k] = pr;
-    if (pr < minp) minp = pr;
+    s_weighted = minp < P.drpm_threshold;
+    if (s_weighted) {   // SolveWithSnrProbabilities, include/degeneracy.h:107-131
+      double tt[6];
+      for (int i = 0; i < 6; ++i) {
+        double sacc = 0.0;
+        for (int r = 0; r < 6; ++r) sacc += st->U[r * 6 + i] * g[r];
+        const double dps = fabs(st->ev[i]) > 1e-10 ? probs[i] / st->ev[i] : 0.0;
+        tt[i] = sacc * dps;
+      }
+      for (int r = 0; r < 6; ++r) {
+        double sacc = 0.0;
+        for (int i = 0; i < 6; ++i) sacc += st->U[r * 6 + i] * tt[i];
+        x[r] = sacc;
+      }
+    }
   }
-  __shared__ double x[6];   // see solve_ldlt6
+  __syncwarp();
   int rank = 6;
-  if (minp < P.drpm_threshold) {   // SolveWithSnrProbabilities, include/degeneracy.h:107-131
-    double tt[6];
-    for (int i = 0; i < 6; ++i) {
-      double sacc = 0.0;
-      for (int r = 0; r < 6; ++r) sacc += st->U[r * 6 + i] * g[r];
-      const double dps = fabs(st->ev[i]) > 1e-10 ? probs[i] / st->ev[i] : 0.0;
-      tt[i] = sacc * dps;
-    }
-    for (int r = 0; r < 6; ++r) {
-      double sacc = 0.0;
-      for (int i = 0; i < 6; ++i) sacc += st->U[r * 6 + i] * tt[i];
-      x[r] = sacc;
-    }
-  } else {
-    rank = solve_ldlt6(H, g, (double)st->pairs, x);   // weighted_A.colPivHouseholderQr().solve(weighted_b), :576
-  }
+  if (!s_weighted) rank = solve_ldlt6_warp(st->H, st->g, scale, (double)st->pairs, x);   // weighted_A.colPivHouseholderQr().solve(weighted_b), :576
   finish_iteration(st, P, x, rank, advance_loop, cond, use_cond);
 }
 

@@ -18,3 +18,12 @@ for it in range(rs["iters"]):
     d = np.diff(st[it]) / 1e3
     gap = (st[it + 1, 0] - st[it, 6]) / 1e3 if it + 1 < rs["iters"] else 0.0
     print(f"it {it}: " + "  ".join(f"{n} {v:7.1f}" for n, v in zip(names, d)) + f"  | to next {gap:5.1f} us")
+
+try:
+    sb = np.zeros(8, np.uint64)
+    ctx.L.plo_debug_solve_stamps.argtypes = [C.c_void_p]
+    ctx.L.plo_debug_solve_stamps(sb.ctypes.data_as(C.c_void_p))
+    d = np.diff(sb[:6].astype(np.int64)) / 1e3
+    print("last solve (us): state copy %.1f  ldlt %.1f  (bookkeeping %.1f)  rodrigues+polar %.1f  compose+tests %.1f" % tuple(d))
+except AttributeError:
+    pass
