@@ -368,13 +368,13 @@ PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_
 /* the same launches one by one (ICP iteration i of the last plo_register -> ms_each[i], at most cap
  * and at most 64 entries): shows how the projection gets cheaper as the pose settles */
 PLO_API int plo_last_project_times(plo_ctx* ctx, float* ms_each, int32_t cap, int32_t* n_project);
-/* per-kernel timing of one projection pass for the roofline: runs the projection kernel
- * `reps` times at the current pose and returns the mean device ms per launch */
 /* per projection of the last plo_register: how many queries k_project_settled could not answer from their candidate
  * tile and handed to the tree walk (-1: the settled kernel did not run in that projection) */
 PLO_API int plo_last_tile_misses(plo_ctx* ctx, int32_t* misses, int32_t cap, int32_t* n_project);
 /* debug builds (-DPLO_LOOP_TIMING) only: phase-boundary timestamps of the resident loop kernel */
 PLO_API int plo_debug_loop_stamps(plo_ctx* ctx, unsigned long long* out128);
+/* per-kernel timing of one projection pass for the roofline: runs the projection kernel
+ * `reps` times at the current pose and returns the mean device ms per launch */
 PLO_API int plo_time_project_kernel(plo_ctx* ctx, const double T[16], int32_t reps, float* ms_mean);
 
 #ifdef __cplusplus

@@ -76,7 +76,7 @@ EXPORTS = [
     "plo_launch_count", "plo_last_timings", "plo_time_project_kernel", "plo_set_profiling",
     "plo_last_kernel_timings", "plo_map_reset", "plo_map_push", "plo_map_push_device", "plo_map_info", "plo_map_get",
     "plo_frontend_default_params", "plo_frontend", "plo_frontend_device", "plo_frontend_get", "plo_frontend_device_records",
-    "plo_set_tuning", "plo_last_tile_misses", "plo_solve_ls_host", "plo_solve_ransac_host", "plo_solve_drpm_host",
+    "plo_set_tuning", "plo_last_tile_misses", "plo_debug_loop_stamps", "plo_solve_ls_host", "plo_solve_ransac_host", "plo_solve_drpm_host",
     "plo_imls_height", "plo_compute_normal", "plo_stream_wait_event",
 ]
 
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.plo_set_tuning.argtypes = [vp, C.c_char_p, i32]
     L.plo_stream_wait_event.argtypes = [vp, vp]
     L.plo_last_tile_misses.argtypes = [vp, vp, i32, C.POINTER(i32)]
+    L.plo_debug_loop_stamps.argtypes = [vp, vp]
     L.plo_solve_ls_host.argtypes = [vp, vp, vp, vp, i64, C.c_double, vp, C.POINTER(i32)]
     L.plo_solve_ransac_host.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PloParams), vp, vp, C.POINTER(i64), C.POINTER(i32)]
     L.plo_solve_drpm_host.argtypes = [vp, vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, vp, vp]
