@@ -30,8 +30,12 @@ constexpr int kSortItems = PLO_SORT_ITEMS;      // keys per thread in the radix-
 constexpr int kSortTile = 256 * kSortItems;     // keys per block
 constexpr int kRadixBits = 10;    // 4 passes over the 39-bit key
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kAxisBits = 13;     // Hilbert cells per axis = 2^13 (3.7 cm on a 300 m cube; ties keep input order)
-constexpr int kKeyBits = 40;
+#ifndef PLO_AXIS_BITS
+#define PLO_AXIS_BITS 13
+#define PLO_KEY_BITS 40
+#endif
+constexpr int kAxisBits = PLO_AXIS_BITS;     // Hilbert cells per axis = 2^13 (3.7 cm on a 300 m cube; ties keep input order)
+constexpr int kKeyBits = PLO_KEY_BITS;
 constexpr int kPasses = kKeyBits / kRadixBits;
 
 __device__ __forceinline__ unsigned f2ord(float f) {

@@ -150,12 +150,12 @@ __device__ __forceinline__ bool query_tail(const MapView& m, const DevParams& P,
   kd2f_out = kd2f_now;
 
   // ---- 1-NN without self match (:601-609) ----
-  int i1 = -1, pos1 = -1;
+  int i1 = -1, pos1 = -1, j1 = -1;   // j1: its place in the list (-1: it came from the second search)
   double d1 = CUDART_INF;
   {
     const unsigned nz = __ballot_sync(PLO_FULL_MASK, has && tk.d2 > DBL_EPSILON);
     if (nz) {
-      const int j1 = __ffs(nz) - 1;
+      j1 = __ffs(nz) - 1;
       i1 = __shfl_sync(PLO_FULL_MASK, tk.idx, j1);
       pos1 = __shfl_sync(PLO_FULL_MASK, tk.pos, j1);
       d1 = __shfl_sync(PLO_FULL_MASK, tk.d2, j1);
@@ -174,14 +174,16 @@ __device__ __forceinline__ bool query_tail(const MapView& m, const DevParams& P,
 
   // ---- per-neighbour data for the IMLS sum (one neighbour per lane) ----
   double pnx = 0.0, pny = 0.0, pnz = 0.0, ddx = 0.0, ddy = 0.0, ddz = 0.0;
-  bool keep = false;
+  bool fin = false, keep = false;
   if (has) {
     if (PCA) { pnx = m.nrm_pca[3 * (size_t)tk.pos]; pny = m.nrm_pca[3 * (size_t)tk.pos + 1]; pnz = m.nrm_pca[3 * (size_t)tk.pos + 2]; }
     else { const float4 nn = __ldg(&m.nrm[tk.pos]); pnx = (double)nn.x; pny = (double)nn.y; pnz = (double)nn.z; }
     ddx = __dsub_rn(qx, (double)pp.x); ddy = __dsub_rn(qy, (double)pp.y); ddz = __dsub_rn(qz, (double)pp.z);
-    keep = finite3d(pnx, pny, pnz);                                           // :436-440 (:396-400 holds by construction)
+    fin = finite3d(pnx, pny, pnz);                                            // :436-440 (:396-400 holds by construction)
+    keep = fin;
     if (keep && P.angle_constraint) keep = !angle_exceeds(xnx, xny, xnz, pnx, pny, pnz, P);   // :442-451
   }
+  const unsigned fin_mask = __ballot_sync(PLO_FULL_MASK, fin), keep_mask = __ballot_sync(PLO_FULL_MASK, keep);
 
   int status = PLO_PT_OK;
   double height = CUDART_NAN;
@@ -191,11 +193,17 @@ __device__ __forceinline__ bool query_tail(const MapView& m, const DevParams& P,
   else {
     if (PCA) { n0x = m.nrm_pca[3 * (size_t)pos1]; n0y = m.nrm_pca[3 * (size_t)pos1 + 1]; n0z = m.nrm_pca[3 * (size_t)pos1 + 2]; }
     else { const float4 nn = __ldg(&m.nrm[pos1]); n0x = (double)nn.x; n0y = (double)nn.y; n0z = (double)nn.z; }   // :630-633
-    if (!finite3d(n0x, n0y, n0z)) status = PLO_PT_INVALID_NORMAL;            // :673-679
-    else if (P.angle_constraint && angle_exceeds(xnx, xny, xnz, n0x, n0y, n0z, P)) status = PLO_PT_NORMAL_CONSTRAINT;   // :681-692
+    if (j1 >= 0) {
+      // the 1-NN is neighbour j1 of the list: its normal went through the same two tests on lane j1 (same operands)
+      if (!((fin_mask >> j1) & 1u)) status = PLO_PT_INVALID_NORMAL;            // :673-679
+      else if (!((keep_mask >> j1) & 1u)) status = PLO_PT_NORMAL_CONSTRAINT;   // :681-692
+    } else {
+      if (!finite3d(n0x, n0y, n0z)) status = PLO_PT_INVALID_NORMAL;
+      else if (P.angle_constraint && angle_exceeds(xnx, xny, xnz, n0x, n0y, n0z, P)) status = PLO_PT_NORMAL_CONSTRAINT;
+    }
   }
   if (status == PLO_PT_OK) {   // warp-uniform
-    const int cnt = __popc(__ballot_sync(PLO_FULL_MASK, keep));
+    const int cnt = __popc(keep_mask);
     if (cnt < 3) status = PLO_PT_MLS_FAIL;               // :463-466, :696-701
     else {
       // :468 — the bandwidth h_max = sqrt(d2[cnt-1]) / 3 indexes the UNFILTERED sorted distance
@@ -206,7 +214,13 @@ __device__ __forceinline__ bool query_tail(const MapView& m, const DevParams& P,
         w = exp(tk.d2 * cinv);                           // :474-475 (diff_norm == d2, same arithmetic)
         pr = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(w, ddx), pnx), __dmul_rn(__dmul_rn(w, ddy), pny)), __dmul_rn(__dmul_rn(w, ddz), pnz));   // :476
       }
-      const double wsum = warp_sum(w), psum = warp_sum(pr);
+      // both butterfly sums (offsets 16, 8, 4, 2, 1 -- the order the oracle follows) in one: after the first exchange the
+      // lower half-warp carries the weights, the upper half the projections; same operand pairs, same bits
+      const bool lower = lane < 16;
+      double acc = (lower ? w : pr) + __shfl_xor_sync(PLO_FULL_MASK, lower ? pr : w, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(PLO_FULL_MASK, acc, o);
+      const double wsum = __shfl_sync(PLO_FULL_MASK, acc, 0), psum = __shfl_sync(PLO_FULL_MASK, acc, 16);
       height = psum / (wsum + 1e-5);                     // :480
       if (!isfinite(height)) status = PLO_PT_NAN_INF_HEIGHT;   // :703-717
     }

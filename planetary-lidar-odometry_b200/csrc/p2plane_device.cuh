@@ -9,6 +9,11 @@
 
 #include "plo_internal.cuh"
 
+#ifndef PLO_WARM_DIST
+#define PLO_WARM_DIST 0.05    // a step below this (m, rad): the next refresh walk stores candidate tiles
+#define PLO_WARM_ANGLE 0.01
+#endif
+
 namespace {
 
 #ifdef PLO_LOOP_TIMING
@@ -254,7 +259,7 @@ __device__ __forceinline__ void finish_iteration(DevState* __restrict__ st, cons
     // small step: the temporal bound is tight, short chunks balance best; large step: only the carry
     // bound along the scan order helps, long chunks amortise the greedy bound of each chunk head
     st->chunk = (dd < 0.05 && da < 0.01) ? PLO_CHUNK_WARM : PLO_CHUNK_COLD;
-    st->warm = (dd < 0.05 && da < 0.01) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
+    st->warm = (dd < PLO_WARM_DIST && da < PLO_WARM_ANGLE) ? 1 : 0;   // k_project: worth widening a refresh walk for the candidate cache
     if (dd < P.delta_dist_thr && da < P.delta_angle_thr) { st->status = PLO_REG_CONVERGED; st->done = 1; }   // :643-646
     else if (st->iters >= P.iterations) { st->status = PLO_REG_MAX_ITERS; st->done = 1; }
     if (use_cond) cudaGraphSetConditional(cond, st->done ? 0 : 1);   // WHILE node: run the body again?

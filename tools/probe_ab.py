@@ -16,6 +16,8 @@ else:
 import torch
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ctx = plo.Context(0)
+for kv in os.environ.get("PLO_TUNE", "").split(","):   # e.g. PLO_TUNE=force_warm=1,group=16
+    if "=" in kv: ctx.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
 regs, idxs = [], []
 for i in range(8):
     ctx.set_target(target); ctx.set_source(source)
