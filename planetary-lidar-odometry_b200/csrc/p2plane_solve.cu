@@ -357,104 +357,154 @@ __device__ __forceinline__ double dist3(const double a[3], const double b[3]) {
   return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
 }
 
-__global__ void __launch_bounds__(1024) k_ransac(const float* __restrict__ src, const float* __restrict__ ref,
-                                                 const float* __restrict__ nrm, const DevCounts* __restrict__ counts,
-                                                 DevState* __restrict__ st, DevParams P, double* __restrict__ mind, int respect_done) {
+// ---- RANSAC hypotheses (src/solver.cpp:229-331), one hypothesis per block, the grid strides over them -------------
+// The reference draws, fits and counts hypothesis after hypothesis and stops at the first one whose inlier count exceeds
+// ransac_min_inliers_percentage.  Hypothesis `it` depends on the random stream only (its first point is draw `it` of
+// xorshift64, the other two follow from farthest-point sampling), so hypotheses are evaluated independently: block b takes
+// it = first + b, first + b + grid, ... in increasing order, writes inlier count and transform of each into the scratch
+// table and lowers `stop` to the smallest `it` that passes the test; a block gives up as soon as its `it` lies beyond
+// `stop` (checked between the three passes over the pairs as well).  Every hypothesis up to the final `stop` is therefore
+// evaluated, and k_ransac_pick replays the reference's sequential rule over the table: same best hypothesis, same count
+// of hypotheses, whatever the grid.  Launched twice per solve: hypothesis 0 alone (in the usual case it already passes,
+// and 295 other blocks reading the pair list would only slow it down), then the rest over the whole GPU -- the worst case
+// (the exit never fires: 5000 hypotheses x three passes over ~130 k pairs) takes a few ms instead of seconds in one block.
+struct RansacScratch {
+  long long* cnt;   // [ransac_max_iterations] inliers of hypothesis it
+  double* T;        // [ransac_max_iterations][16]
+  int* stop;        // smallest `it` whose count passes the exit test; INT_MAX while none does
+};
+
+__global__ void __launch_bounds__(1024) k_ransac_eval(const float* __restrict__ src, const float* __restrict__ ref,
+                                                      const float* __restrict__ nrm, const DevCounts* __restrict__ counts,
+                                                      const DevState* __restrict__ st, DevParams P, RansacScratch rs, int it_first,
+                                                      int it_end, int respect_done) {
   if (respect_done && st->done) return;
   __shared__ double s_val[32];
   __shared__ int s_idx[32];
   __shared__ long long s_cnt[32];
   __shared__ double s_T[16];
   __shared__ int s_sel[3];
-  __shared__ int s_stop;
+  __shared__ int s_stop[3];   // `stop` as thread 0 saw it before each pass (one slot per check: no write races a read)
   const int n = counts->n_pairs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  volatile int* vstop = rs.stop;
+  if (it_first == 0 && blockIdx.x == 0 && tid == 0) *vstop = INT_MAX;   // first launch of this solve (one block)
+  if (n <= 0) return;
+  const int min_inliers = (int)(P.ransac_min_inliers_pct * (double)n);   // :238
   unsigned long long rng = P.ransac_seed;
-  long long best = 0;
-  double Tbest[16];
-  for (int i = 0; i < 16; ++i) Tbest[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  int iters = 0;
-  if (n > 0) {
-    const int min_inliers = (int)(P.ransac_min_inliers_pct * (double)n);   // :238
-    for (int it = 0; it < P.ransac_max_iterations; ++it) {   // :244
-      // ---- farthestPointSampling(source_cloud, 3), src/common.cpp:19-82 ----
-      if (tid == 0) {
-        rng = xorshift64(rng);
-        s_sel[0] = (int)(rng % (unsigned long long)n);
-        s_stop = 0;
+  int drawn = 0;
+  for (int it = it_first + (int)blockIdx.x; it < it_end; it += (int)gridDim.x) {   // :244
+    // ---- farthestPointSampling(source_cloud, 3), src/common.cpp:19-82 ----
+    if (tid == 0) {
+      for (; drawn <= it; ++drawn) rng = xorshift64(rng);   // draw `it` of the stream
+      s_sel[0] = (int)(rng % (unsigned long long)n);
+      s_stop[0] = (it_first > 0 || it > 0) ? *vstop : INT_MAX;
+    }
+    __syncthreads();
+    if (s_stop[0] < it) break;
+    const int first = s_sel[0];
+    double pf[3];
+    load3(src, first, pf);
+    double bv = -1.0;
+    int bi = -1;
+    for (int i = tid; i < n; i += 1024) {
+      double pi[3];
+      load3(src, i, pi);
+      const double d = dist3(pf, pi);
+      if (i != first && d > bv) { bv = d; bi = i; }
+    }
+    if (tid == 0) s_stop[1] = *vstop;
+    block_argmax(bv, bi, s_val, s_idx, &s_sel[1]);
+    if (s_stop[1] < it) break;
+    int second = s_sel[1];
+    const bool have_second = second >= 0;
+    if (!have_second) second = first;
+    double ps[3];
+    load3(src, second, ps);
+    bv = -1.0;
+    bi = -1;
+    for (int i = tid; i < n; i += 1024) {
+      double pi[3];
+      load3(src, i, pi);
+      double m = dist3(pf, pi);   // distance to the chosen set (recomputed: no per-hypothesis array)
+      if (have_second) {
+        const double d = dist3(ps, pi);
+        if (d < m) m = d;
       }
-      __syncthreads();
-      const int first = s_sel[0];
-      double pf[3];
-      load3(src, first, pf);
-      double bv = -1.0;
-      int bi = -1;
-      for (int i = tid; i < n; i += 1024) {
-        double pi[3];
-        load3(src, i, pi);
-        const double d = dist3(pf, pi);
-        mind[i] = d;
-        if (i != first && d > bv) { bv = d; bi = i; }
-      }
-      block_argmax(bv, bi, s_val, s_idx, &s_sel[1]);
-      int second = s_sel[1];
-      const bool have_second = second >= 0;
-      if (!have_second) second = first;
-      double ps[3];
-      load3(src, second, ps);
-      bv = -1.0;
-      bi = -1;
-      for (int i = tid; i < n; i += 1024) {
-        double m = mind[i];
-        if (have_second) {
-          double pi[3];
-          load3(src, i, pi);
-          const double d = dist3(ps, pi);
-          if (d < m) { m = d; mind[i] = m; }
-        }
-        if (i != first && i != second && m > bv) { bv = m; bi = i; }
-      }
-      block_argmax(bv, bi, s_val, s_idx, &s_sel[2]);
-      if (tid == 0) {
-        int ids[3] = {first, second, s_sel[2] >= 0 ? s_sel[2] : first};
-        double A[3][6], b[3], x[6];
-        for (int r = 0; r < 3; ++r) {   // :255-270
-          double sv[3], dv[3], nv[3];
-          load3(src, ids[r], sv); load3(ref, ids[r], dv); load3(nrm, ids[r], nv);
-          ab_row(sv, dv, nv, A[r], b[r]);
-        }
-        colpiv_qr_solve_3x6(A, b, x);   // :273
-        double D[16];
-        delta_from_x(x, D);             // :276-298
-        for (int i = 0; i < 16; ++i) s_T[i] = D[i];
-      }
-      __syncthreads();
-      // ---- inlier count, :300-314 ----
-      double T[16];
-      for (int i = 0; i < 16; ++i) T[i] = s_T[i];
-      long long cnt = 0;
-      for (int i = tid; i < n; i += 1024) {
+      if (i != first && i != second && m > bv) { bv = m; bi = i; }
+    }
+    block_argmax(bv, bi, s_val, s_idx, &s_sel[2]);
+    if (tid == 0) {
+      int ids[3] = {first, second, s_sel[2] >= 0 ? s_sel[2] : first};
+      double A[3][6], b[3], x[6];
+      for (int r = 0; r < 3; ++r) {   // :255-270
         double sv[3], dv[3], nv[3];
-        load3(src, i, sv); load3(ref, i, dv); load3(nrm, i, nv);
-        cnt += (plane_distance(T, sv, dv, nv) < P.ransac_dist_thr) ? 1 : 0;
+        load3(src, ids[r], sv); load3(ref, ids[r], dv); load3(nrm, ids[r], nv);
+        ab_row(sv, dv, nv, A[r], b[r]);
       }
+      colpiv_qr_solve_3x6(A, b, x);   // :273
+      double D[16];
+      delta_from_x(x, D);             // :276-298
+      for (int i = 0; i < 16; ++i) s_T[i] = D[i];
+      s_stop[2] = *vstop;
+    }
+    __syncthreads();
+    if (s_stop[2] < it) break;
+    // ---- inlier count, :300-314 ----
+    double T[16];
+    for (int i = 0; i < 16; ++i) T[i] = s_T[i];
+    long long cnt = 0;
+    for (int i = tid; i < n; i += 1024) {
+      double sv[3], dv[3], nv[3];
+      load3(src, i, sv); load3(ref, i, dv); load3(nrm, i, nv);
+      cnt += (plane_distance(T, sv, dv, nv) < P.ransac_dist_thr) ? 1 : 0;
+    }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(PLO_FULL_MASK, cnt, o);
-      if (lane == 0) s_cnt[warp] = cnt;
-      __syncthreads();
-      if (tid == 0) {
-        long long total = 0;
-        for (int w = 0; w < 32; ++w) total += s_cnt[w];
-        if (total > best) { best = total; for (int i = 0; i < 16; ++i) Tbest[i] = s_T[i]; }   // :317-320
-        if (best > (long long)min_inliers) s_stop = 1;                                       // :323-325
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(PLO_FULL_MASK, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      long long total = 0;
+      for (int w = 0; w < 32; ++w) total += s_cnt[w];
+      rs.cnt[it] = total;
+      for (int i = 0; i < 16; ++i) rs.T[(size_t)it * 16 + i] = s_T[i];
+      if (total > (long long)min_inliers) atomicMin(rs.stop, it);   // :323-325
+    }
+    __syncthreads();
+  }
+}
+
+// the reference's sequential bookkeeping over the table (one warp): best = first hypothesis with the largest count among
+// those drawn, drawing ends with the first hypothesis after which best > min_inliers (:317-325)
+__global__ void __launch_bounds__(32) k_ransac_pick(const DevCounts* __restrict__ counts, DevState* __restrict__ st, DevParams P,
+                                                    RansacScratch rs, int respect_done) {
+  if (respect_done && st->done) return;
+  const int n = counts->n_pairs;
+  const int lane = threadIdx.x;
+  long long best = 0;
+  int best_it = -1, iters = 0;
+  if (n > 0) {
+    for (int base = 0; base < P.ransac_max_iterations; base += 32) {
+      const int it = base + lane;
+      const bool in = it < P.ransac_max_iterations;
+      // entries beyond the first passing one may never have been written: read one at a time up to it
+      const int stop = *rs.stop;
+      long long v = (in && it <= stop) ? rs.cnt[it] : -1;
+      int vi = it;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long ov = __shfl_xor_sync(PLO_FULL_MASK, v, o);
+        const int oi = __shfl_xor_sync(PLO_FULL_MASK, vi, o);
+        if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
       }
-      iters = it + 1;
-      __syncthreads();
-      if (s_stop) break;
+      if (v > best) { best = v; best_it = vi; }
+      const int last = min(min(base + 31, P.ransac_max_iterations - 1), stop);
+      iters = last + 1;
+      if (stop <= base + 31) break;
     }
   }
-  if (tid == 0) {
-    for (int i = 0; i < 16; ++i) st->Tbest[i] = Tbest[i];
+  if (lane < 16) st->Tbest[lane] = best_it >= 0 ? rs.T[(size_t)best_it * 16 + lane] : ((lane % 5 == 0) ? 1.0 : 0.0);
+  if (lane == 0) {
     st->ransac_best = best;
     st->ransac_iters = iters;
   }
@@ -809,7 +859,7 @@ int plo_reserve_solver_buffers(plo_ctx* c) {
     PLO_CUDA(c, c->h_nrm.reserve(sizeof(double) * 3 * m));
     PLO_CUDA(c, c->h_w.reserve(sizeof(double) * m));
     PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * ((m + kTile - 1) / kTile + 1)));
-    PLO_CUDA(c, c->ransac_mind.reserve(sizeof(double) * m));
+    PLO_CUDA(c, c->ransac_mind.reserve((sizeof(long long) + 16 * sizeof(double)) * (size_t)std::max(c->dprm.ransac_max_iterations, 1) + 64));   // RansacScratch
     PLO_CUDA(c, c->partials2.reserve(sizeof(double) * kNoiseSums * (size_t)plo_grid(c, 2)));
   }
   return PLO_OK;
@@ -836,9 +886,18 @@ int plo_launch_reduce_solve(plo_ctx* c, bool advance_loop, unsigned long long co
   if (ransac) {
     // the hypothesis sampler works on the compacted pair list (indices = positions in source_cloud)
     PLO_TRY(plo_launch_compact_pairs(c, c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->h_w.as<int32_t>()));
-    k_ransac<<<1, 1024, 0, c->stream>>>(c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->counts.as<DevCounts>(),
-                                        c->state.as<DevState>(), P, c->ransac_mind.as<double>(), adv);
-    c->launches++;
+    const int maxit = P.ransac_max_iterations;
+    RansacScratch rs;
+    rs.cnt = c->ransac_mind.as<long long>();
+    rs.T = reinterpret_cast<double*>(rs.cnt + maxit);
+    rs.stop = reinterpret_cast<int*>(rs.T + (size_t)16 * maxit);
+    k_ransac_eval<<<1, 1024, 0, c->stream>>>(c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(), c->counts.as<DevCounts>(),
+                                             c->state.as<DevState>(), P, rs, 0, maxit < 1 ? maxit : 1, adv);
+    if (maxit > 1)
+      k_ransac_eval<<<std::min(maxit - 1, 2 * c->sm_count), 1024, 0, c->stream>>>(c->h_src.as<float>(), c->h_ref.as<float>(), c->h_nrm.as<float>(),
+                                                                                  c->counts.as<DevCounts>(), c->state.as<DevState>(), P, rs, 1, maxit, adv);
+    k_ransac_pick<<<1, 32, 0, c->stream>>>(c->counts.as<DevCounts>(), c->state.as<DevState>(), P, rs, adv);
+    c->launches += maxit > 1 ? 3 : 2;
     PLO_CUDA(c, cudaGetLastError());
   }
   if (advance_loop && c->tune_fuse && c->dprm.solver == PLO_SOLVER_WLS) {

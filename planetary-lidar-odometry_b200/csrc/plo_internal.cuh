@@ -165,7 +165,7 @@ struct plo_ctx {
   // reduction / solve
   DevBuf partials, state, counts, scratch, reduce_ticket, loop_barrier;
   DevBuf ls_keys[2], ls_vals[2], ls_hist, ls_tot, ls_mask;   // trimmed-LS selection
-  DevBuf ransac_mind, partials2;                              // RANSAC FPS distances, DRPM noise partials
+  DevBuf ransac_mind, partials2;                              // RANSAC hypothesis table (RansacScratch), DRPM noise partials
   DevBuf h_src, h_ref, h_nrm, h_w;   // plo_solve_wls_host staging
   DevBuf h_wext, counts_saved;       // host-vector LS / RANSAC / DRPM entry points: caller weights, the context's own counts
   const double* host_w = nullptr;    // != nullptr while such a call runs with caller weights

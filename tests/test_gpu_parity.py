@@ -751,6 +751,21 @@ def test_ransac_front_and_drpm_tail(oracle_mod, final):
     delta2, info2 = ctx.solve_ransac()
     ok, Do2 = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(**kw2))
     assert info2["hypotheses"] == 7 and np.abs(delta2 - Do2).max() < 1e-9
+    # the exit test never fires: 700 hypotheses, spread over the whole GPU (one per block, k_ransac_eval), must give what
+    # the reference's one-after-the-other loop gives; then an inlier bar only the best of them passes: drawing stops there
+    kw3 = dict(kw2, ransac_min_inliers_percentage=1.0, ransac_max_iterations=700)
+    ctx.set_params(plo.default_params(**kw3))
+    ctx.project(np.eye(4))
+    delta3, info3 = ctx.solve_ransac()
+    ok, Do3 = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(**kw3))
+    assert info3["hypotheses"] == 700 and np.abs(delta3 - Do3).max() < 1e-9
+    kw4 = dict(kw3, ransac_min_inliers_percentage=(info3["inliers"] - 0.5) / pr["n"])
+    ctx.set_params(plo.default_params(**kw4))
+    ctx.project(np.eye(4))
+    delta4, info4 = ctx.solve_ransac()
+    ok, Do4 = oracle_mod.solve_ransac(s, d, n, oracle_mod.default_params(**kw4))
+    assert 1 <= info4["hypotheses"] <= 700 and info4["inliers"] == info3["inliers"]
+    assert np.abs(delta4 - Do4).max() < 1e-9 and np.array_equal(delta4, delta3)
     # full loop (resident graph) against the oracle's loop with the same solver chain
     ctx3, orc3 = _both(oracle_mod, pair.target, pair.source, **kw)
     Tg, sg = ctx3.register()
