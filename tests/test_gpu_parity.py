@@ -552,6 +552,55 @@ def test_cfg2_sequence_201_frames_ate_tum_and_oracle_parity(oracle_mod, tmp_path
         assert np.abs(R - P[k, :3, :3]).max() < 5e-6      # 6-decimal quaternion components
 
 
+def test_cfg2_sequence_1000_frames_full_length(oracle_mod):
+    """BASELINE config 2 at its stated length: 1000 full-size VLP-32C frames (999 registrations) through LaserOdometry on
+    the resident path -- every registration converges, poses chain bit for bit, oracle parity (iterations, status, pairs,
+    pose) on every 100th registration, ATE below 1 % of the path.  The summary goes to gpurun_out/ when that exists."""
+    import json
+    import os
+    import time
+    n = 1000
+    fs = W.generate_sequences([2001], n)[0]
+    frames = [fs.frame(k) for k in range(n)]
+    odo = plo.LaserOdometry(resident=True)
+    odo.run(frames[:3])     # allocations, graph instantiation
+    odo = plo.LaserOdometry(resident=True)
+    t0 = time.perf_counter()
+    P = odo.run(frames)
+    run_s = time.perf_counter() - t0
+    cur = np.eye(4)
+    for k in range(1, n):
+        st = odo.frame_stats[k]
+        assert st["status"] == 1, (k, st["status_name"])
+        cur = cur @ st["rPose"]
+        assert np.array_equal(cur, P[k]), k
+    orc = oracle_mod.Oracle()
+    worst_t = worst_r = 0.0
+    for k in range(100, n, 100):
+        orc.set_target(frames[k - 1])
+        orc.set_source(frames[k])
+        To, so = orc.register()
+        st = odo.frame_stats[k]
+        assert st["iters"] == so["iters"] and st["status"] == so["status"] and st["pairs"] == so["pairs"], k
+        worst_t = max(worst_t, float(np.linalg.norm(st["rPose"][:3, 3] - To[:3, 3])))
+        worst_r = max(worst_r, _rot_err(st["rPose"][:3, :3], To[:3, :3]))
+    assert worst_r < POSE_RAD and worst_t < POSE_M
+    gt = np.stack([np.linalg.inv(fs.poses[0]) @ T for T in fs.poses])
+    err = np.linalg.norm(P[:, :3, 3] - gt[:, :3, 3], axis=1)
+    ate = float(np.sqrt(np.mean(err ** 2)))
+    path_len = float(np.sum(np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1)))
+    assert path_len > 500.0 and ate < 0.01 * path_len, (ate, path_len)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        res = {"workload": "BASELINE config 2: 1000-frame VLP-32C sequence, synthetic, seed 2001", "registrations": n - 1,
+               "points_per_frame_mean": float(np.mean([f.shape[0] for f in frames])), "wall_s_host_frames_one_at_a_time": run_s,
+               "scans_per_s_wall": (n - 1) / run_s, "mean_iters": float(np.mean([odo.frame_stats[k]["iters"] for k in range(1, n)])),
+               "path_length_m": path_len, "ate_rmse_m": ate, "end_point_error_m": float(err[-1]),
+               "oracle_parity_every_100th": {"max_trans_diff_m": worst_t, "max_rot_diff_rad": worst_r}}
+        with open(os.path.join(out_dir, "cfg2_1000_frames.json"), "w", encoding="utf-8") as f:
+            f.write(json.dumps(res) + "\n")
+
+
 def test_cfg4_five_million_point_map(oracle_mod):
     """BASELINE config 4 (HDL-64 frame vs 5 M-point map: index build + radius-search stress, 4 tree levels):
     iteration-0 neighbour sets against the oracle on a query subset, full-loop pose parity, index-size properties."""
