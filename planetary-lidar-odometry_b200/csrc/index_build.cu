@@ -98,17 +98,25 @@ __global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ r
       hi[a] = fmaxf(hi[a], __shfl_xor_sync(PLO_FULL_MASK, hi[a], o));
     }
   }
+  __shared__ float s_lo[8][3], s_hi[8][3];
   if (lane == 0) {
     s_cnt[warp] = cnt;
-    if (bbox != nullptr && cnt > 0) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        atomicMin(&bbox[a], f2ord(lo[a]));
-        atomicMax(&bbox[3 + a], f2ord(hi[a]));
-      }
-    }
+    for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
   }
   __syncthreads();
+  // one atomic per block and bound (per warp they were 47 k atomics on six addresses: the kernel's critical path)
+  if (bbox != nullptr && threadIdx.x < 6) {
+    const int a = threadIdx.x % 3;
+    const bool is_max = threadIdx.x >= 3;
+    float v = is_max ? -CUDART_INF_F : CUDART_INF_F;
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (s_cnt[w] > 0) { any = true; v = is_max ? fmaxf(v, s_hi[w][a]) : fminf(v, s_lo[w][a]); }
+    }
+    if (any) { if (is_max) atomicMax(&bbox[3 + a], f2ord(v)); else atomicMin(&bbox[a], f2ord(v)); }
+  }
   if (threadIdx.x == 0) {
     int t = 0;
 #pragma unroll
