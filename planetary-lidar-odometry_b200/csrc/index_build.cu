@@ -52,6 +52,7 @@ __device__ __forceinline__ bool finite3(float x, float y, float z) {
 
 // bbox[0..2] = min (ordered uint), bbox[3..5] = max
 __global__ void k_init_bbox(unsigned* bbox) {
+  PLO_CHAIN_ENTER();
   if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
   else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
 }
@@ -61,6 +62,7 @@ __global__ void k_init_bbox(unsigned* bbox) {
 __global__ void __launch_bounds__(256) k_unpack_count(const char* __restrict__ rec, int stride, int n, int vec16,
                                                       float4* __restrict__ praw, float4* __restrict__ nraw,
                                                       int* __restrict__ blockcnt, unsigned* __restrict__ bbox) {
+  PLO_CHAIN_ENTER();
   __shared__ int s_cnt[8];
   const int base = blockIdx.x * kTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -162,6 +164,7 @@ __device__ __forceinline__ unsigned long long hilbert_key(unsigned x0, unsigned 
 __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ praw, int n, const int* __restrict__ blockoff,
                                               const unsigned* __restrict__ bbox, int* __restrict__ cidx,
                                               unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  PLO_CHAIN_ENTER();
   const int base = blockIdx.x * kTile;
   bool fin[kTile / 256];
   float4 p[kTile / 256];
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ praw, i
 __global__ void __launch_bounds__(256) k_compact_source(const float4* __restrict__ praw, const float4* __restrict__ nraw, int n,
                                                         const int* __restrict__ blockoff, float4* __restrict__ sp,
                                                         float4* __restrict__ sn) {
+  PLO_CHAIN_ENTER();
   const int base = blockIdx.x * kTile;
   bool fin[kTile / 256];
   float4 p[kTile / 256];
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(256) k_compact_source(const float4* __restrict
 
 __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __restrict__ keys, int n, int shift,
                                                    int nb, int* __restrict__ hist, int* __restrict__ digit_total) {
+  PLO_CHAIN_ENTER();
   __shared__ int s_h[kRadix];
   for (int d = threadIdx.x; d < kRadix; d += 256) s_h[d] = 0;
   __syncthreads();
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(const unsigned long long* __r
 // one block per digit: base = sum of the totals of all smaller digits, then an exclusive scan of the
 // digit's row (one entry per sort block) — replaces a single-block scan of the whole table
 __global__ void __launch_bounds__(256) k_sort_scan(int* __restrict__ hist, int nb, const int* __restrict__ digit_total) {
+  PLO_CHAIN_ENTER();
   __shared__ int s_warp[8];
   __shared__ int s_carry;
   const int d = blockIdx.x;
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned long long* 
                                                       unsigned long long* __restrict__ keys_out,
                                                       int* __restrict__ vals_out, int n, int shift, int nb,
                                                       const int* __restrict__ hist_scanned) {
+  PLO_CHAIN_ENTER();
   __shared__ int s_w[8][kRadix];   // per-warp running digit counts -> exclusive over warps
   __shared__ int s_g[kRadix];      // global base of (digit, this block)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -354,6 +361,7 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const int* __restrict__ v
                                                        int n_raw, int n_pad, int n_leaf_pad, float4* __restrict__ pts,
                                                        float4* __restrict__ nrm, int* __restrict__ pos_of_cidx,
                                                        float4* __restrict__ lo0, float4* __restrict__ hi0) {
+  PLO_CHAIN_ENTER();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int leaf = blockIdx.x * wpb + (threadIdx.x >> 5); leaf < n_leaf_pad; leaf += gridDim.x * wpb) {
@@ -398,6 +406,7 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const int* __restrict__ v
 __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ lo_c, const float4* __restrict__ hi_c,
                                                      int n_child_pad, float4* __restrict__ lo_p,
                                                      float4* __restrict__ hi_p, int n_par_pad) {
+  PLO_CHAIN_ENTER();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int par = blockIdx.x * wpb + (threadIdx.x >> 5); par < n_par_pad; par += gridDim.x * wpb) {
@@ -528,15 +537,15 @@ int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stri
   cudaStream_t s = c->stream;
   const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
   if (c->ev[0]) cudaEventRecord(c->ev[0], s);
-  k_init_bbox<<<1, 32, 0, s>>>(c->bbox.as<unsigned>());
+  PLO_CUDA(c, plo_launch_chained(k_init_bbox, dim3(1), dim3(32), s, c->bbox.as<unsigned>()));
   LAUNCH_CHECK(c);
-  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, vec16, c->t_praw.as<float4>(),
-                                    c->t_nraw.as<float4>(), c->blockcnt.as<int>(), c->bbox.as<unsigned>());
+  PLO_CUDA(c, plo_launch_chained(k_unpack_count, dim3(nb), dim3(256), s, static_cast<const char*>(dev_records), stride, (int)n, vec16, c->t_praw.as<float4>(),
+                                    c->t_nraw.as<float4>(), c->blockcnt.as<int>(), c->bbox.as<unsigned>()));
   LAUNCH_CHECK(c);
-  k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_target);
+  PLO_CUDA(c, plo_launch_chained(k_scan_exclusive, dim3(1), dim3(1024), s, c->blockcnt.as<int>(), nb, &dc->n_target));
   LAUNCH_CHECK(c);
-  k_keys<<<nb, 256, 0, s>>>(c->t_praw.as<float4>(), (int)n, c->blockcnt.as<int>(), c->bbox.as<unsigned>(),
-                            c->t_cidx.as<int>(), c->keys[0].as<unsigned long long>(), c->vals[0].as<int>());
+  PLO_CUDA(c, plo_launch_chained(k_keys, dim3(nb), dim3(256), s, c->t_praw.as<float4>(), (int)n, c->blockcnt.as<int>(), c->bbox.as<unsigned>(),
+                            c->t_cidx.as<int>(), c->keys[0].as<unsigned long long>(), c->vals[0].as<int>()));
   LAUNCH_CHECK(c);
   int cur = 0;
   PLO_CUDA(c, c->digit_total.reserve(sizeof(int) * kPasses * kRadix));
@@ -544,29 +553,30 @@ int plo_build_index(plo_ctx* c, const void* dev_records, int64_t n, int32_t stri
   for (int pass = 0; pass < kPasses; ++pass) {
     const int shift = pass * kRadixBits;
     int* tot = c->digit_total.as<int>() + pass * kRadix;
-    k_sort_hist<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), (int)n, shift, nbs, c->hist.as<int>(), tot);
+    PLO_CUDA(c, plo_launch_chained(k_sort_hist, dim3(nbs), dim3(256), s, c->keys[cur].as<unsigned long long>(), (int)n, shift, nbs,
+                                   c->hist.as<int>(), tot));
     LAUNCH_CHECK(c);
-    k_sort_scan<<<kRadix, 256, 0, s>>>(c->hist.as<int>(), nbs, tot);
+    PLO_CUDA(c, plo_launch_chained(k_sort_scan, dim3(kRadix), dim3(256), s, c->hist.as<int>(), nbs, tot));
     LAUNCH_CHECK(c);
-    k_sort_scatter<<<nbs, 256, 0, s>>>(c->keys[cur].as<unsigned long long>(), c->vals[cur].as<int>(),
-                                       c->keys[cur ^ 1].as<unsigned long long>(), c->vals[cur ^ 1].as<int>(), (int)n,
-                                       shift, nbs, c->hist.as<int>());
+    PLO_CUDA(c, plo_launch_chained(k_sort_scatter, dim3(nbs), dim3(256), s, c->keys[cur].as<unsigned long long>(), c->vals[cur].as<int>(),
+                                   c->keys[cur ^ 1].as<unsigned long long>(), c->vals[cur ^ 1].as<int>(), (int)n, shift, nbs,
+                                   c->hist.as<int>()));
     LAUNCH_CHECK(c);
     cur ^= 1;
   }
   {
     const int64_t warps = pad[0];
     const int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)plo_grid(c, 16));
-    k_gather_leaves<<<blocks, 256, 0, s>>>(c->vals[cur].as<int>(), c->t_praw.as<float4>(), c->t_nraw.as<float4>(),
+    PLO_CUDA(c, plo_launch_chained(k_gather_leaves, dim3(blocks), dim3(256), s, c->vals[cur].as<int>(), c->t_praw.as<float4>(), c->t_nraw.as<float4>(),
                                            c->t_cidx.as<int>(), (int)n, (int)n_pad, (int)pad[0], c->pts_sorted.as<float4>(),
                                            c->nrm_sorted.as<float4>(), c->pos_of_cidx.as<int>(),
-                                           c->lvl_lo[0].as<float4>(), c->lvl_hi[0].as<float4>());
+                                           c->lvl_lo[0].as<float4>(), c->lvl_hi[0].as<float4>()));
     LAUNCH_CHECK(c);
   }
   for (int l = 1; l < L; ++l) {
     const int blocks = (int)std::min<int64_t>((pad[l] + 7) / 8, (int64_t)plo_grid(c, 16));
-    k_build_level<<<blocks, 256, 0, s>>>(c->lvl_lo[l - 1].as<float4>(), c->lvl_hi[l - 1].as<float4>(), (int)pad[l - 1],
-                                         c->lvl_lo[l].as<float4>(), c->lvl_hi[l].as<float4>(), (int)pad[l]);
+    PLO_CUDA(c, plo_launch_chained(k_build_level, dim3(blocks), dim3(256), s, c->lvl_lo[l - 1].as<float4>(), c->lvl_hi[l - 1].as<float4>(), (int)pad[l - 1],
+                                         c->lvl_lo[l].as<float4>(), c->lvl_hi[l].as<float4>(), (int)pad[l]));
     LAUNCH_CHECK(c);
   }
   if (c->ev[1]) { cudaEventRecord(c->ev[1], s); c->ev_index_pending = true; }
@@ -623,13 +633,13 @@ int plo_upload_source(plo_ctx* c, const void* dev_records, int64_t n, int32_t st
   PLO_CUDA(c, c->blockcnt.reserve(sizeof(int) * (size_t)(nb + 1)));
   cudaStream_t s = c->stream;
   const int vec16 = (stride >= 32 && stride % 16 == 0 && reinterpret_cast<uintptr_t>(dev_records) % 16 == 0) ? 1 : 0;
-  k_unpack_count<<<nb, 256, 0, s>>>(static_cast<const char*>(dev_records), stride, (int)n, vec16, c->s_praw.as<float4>(),
-                                    c->s_nraw.as<float4>(), c->blockcnt.as<int>(), nullptr);
+  PLO_CUDA(c, plo_launch_chained(k_unpack_count, dim3(nb), dim3(256), s, static_cast<const char*>(dev_records), stride, (int)n, vec16, c->s_praw.as<float4>(),
+                                    c->s_nraw.as<float4>(), c->blockcnt.as<int>(), nullptr));
   LAUNCH_CHECK(c);
-  k_scan_exclusive<<<1, 1024, 0, s>>>(c->blockcnt.as<int>(), nb, &dc->n_source);
+  PLO_CUDA(c, plo_launch_chained(k_scan_exclusive, dim3(1), dim3(1024), s, c->blockcnt.as<int>(), nb, &dc->n_source));
   LAUNCH_CHECK(c);
-  k_compact_source<<<nb, 256, 0, s>>>(c->s_praw.as<float4>(), c->s_nraw.as<float4>(), (int)n, c->blockcnt.as<int>(),
-                                      c->s_p.as<float4>(), c->s_n.as<float4>());
+  PLO_CUDA(c, plo_launch_chained(k_compact_source, dim3(nb), dim3(256), s, c->s_praw.as<float4>(), c->s_nraw.as<float4>(), (int)n, c->blockcnt.as<int>(),
+                                      c->s_p.as<float4>(), c->s_n.as<float4>()));
   LAUNCH_CHECK(c);
   c->have_source = true;
   return PLO_OK;

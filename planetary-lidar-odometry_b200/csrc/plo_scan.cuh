@@ -6,10 +6,46 @@
 
 namespace {
 
+// Programmatic dependent launch (index build, source upload): these kernels are short (2-25 us) and strictly chained, so
+// much of what separates them is launch latency.  A kernel launched through plo_launch_chained() may have its blocks
+// scheduled while the previous grid is still draining; PLO_CHAIN_ENTER() at its very top waits until that grid has
+// completed and its writes are visible (griddepcontrol.wait -- the ordering a plain stream launch gives, nothing is read
+// or written before it), then lets the NEXT kernel of the chain be scheduled behind this one.  Launched the ordinary way
+// both instructions do nothing.
+#ifdef PLO_CHAIN_EARLY   // experiment: release the successor before waiting (a deeper cascade of resident, waiting grids)
+#define PLO_CHAIN_ENTER()                                         \
+  do {                                                            \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    asm volatile("griddepcontrol.wait;" ::: "memory");            \
+  } while (0)
+#else
+#define PLO_CHAIN_ENTER()                                         \
+  do {                                                            \
+    asm volatile("griddepcontrol.wait;" ::: "memory");            \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t plo_launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kTile = 1024;   // elements per block in the compaction kernels (256 threads x 4)
 
 // in-place exclusive scan of a small int array by one block; total -> *total_out
 __global__ void __launch_bounds__(1024) k_scan_exclusive(int* __restrict__ data, int n, int* __restrict__ total_out) {
+  PLO_CHAIN_ENTER();
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   constexpr int kPer = 8;
