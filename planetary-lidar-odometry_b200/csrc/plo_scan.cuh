@@ -2,6 +2,8 @@
 // index build and the pair compaction (internal linkage: included by several .cu files).
 #pragma once
 
+#include <cstdlib>
+
 #include "plo_internal.cuh"
 
 namespace {
@@ -37,7 +39,8 @@ static inline cudaError_t plo_launch_chained(void (*kernel)(KArgs...), dim3 grid
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool plain = getenv("PLO_NO_CHAIN") != nullptr;   // debugging / A-B: ordinary stream launches
+  cfg.numAttrs = plain ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -1,10 +1,9 @@
 """Front-end (plo_frontend) timing on one HDL-64 scan: device-resident input, wall clock around 20 runs."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "py"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import plo_b200 as plo
-import oracle_ctypes as orc
 pair = plo.synth.workloads.hdl64_pair()
 pts = np.ascontiguousarray(pair.source[:, 0:3])
 ctx = plo.Context(0)
@@ -18,4 +17,3 @@ for _ in range(20):
     st = ctx.frontend(dev, fetch=False)       # stats read-back = one sync per run
 dt = (time.perf_counter() - t) / 20
 print("points", pts.shape[0], "->", st["n"], "gpu ms/scan", dt * 1e3, "launches/scan", (ctx.launch_count - l0) / 20)
-t = time.perf_counter(); o = orc.frontend(pts); print("cpu oracle ms/scan (1 thread, brute-force ring NN)", (time.perf_counter() - t) * 1e3)

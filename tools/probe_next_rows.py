@@ -2,10 +2,9 @@
 loop, local-map push, front-end.  Device-resident inputs; wall clock around synchronous calls, median of 10."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "py"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import plo_b200 as plo
-import oracle_ctypes as orc
 
 def med(f, n=10, warm=2):
     for _ in range(warm): f()
@@ -39,11 +38,9 @@ ms = med(lambda: (ctx2.map_push(frame, T, max_queue=8, transform_normals=True), 
 fr, pts = ctx2.map_info()
 print(f"map_push: queue {fr} frames / {pts} points: {ms:.3f} ms per push (index build alone {ctx2.last_timings()['ms_index_build']:.3f} ms); "
       f"set_target of the same {pts} points from the host costs the upload of {pts * 48 / 1e6:.0f} MB instead of {frame.shape[0] * 48 / 1e6:.1f} MB")
-t = time.perf_counter(); q = orc.transform_to_end(pair.target, T, True); print(f"cpu oracle TransformToEnd of {pair.target.shape[0]} points: {1e3 * (time.perf_counter() - t):.1f} ms (1 thread)")
 # front-end
 raw = torch.from_numpy(np.ascontiguousarray(pair.source[:, 0:3])).cuda()
 out = {}
 def fe(): out["s"] = ctx.frontend(raw, fetch=False)
 ms = med(fe)
 print(f"frontend: {raw.shape[0]} raw points -> {out['s']['n']} filtered, {out['s']['candidates']} presampled: {ms:.3f} ms per scan (16 launches, one sync)")
-t = time.perf_counter(); o = orc.frontend(pair.source[:, 0:3]); print(f"cpu oracle frontend: {1e3 * (time.perf_counter() - t):.0f} ms (1 thread, brute-force ring NN)")
