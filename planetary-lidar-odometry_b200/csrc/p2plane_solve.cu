@@ -730,8 +730,9 @@ __global__ void __launch_bounds__(256) k_ls_select(const int* __restrict__ vals_
     mask[vals_sorted[j]] = (j >= lower && j <= upper) ? 1 : 0;
 }
 
-__global__ void k_init_state(DevState* st, const double* T0, int use_prev, int force_warm) {
+__global__ void k_init_state(DevState* st, const double* T0, int use_prev, int force_warm, unsigned* loop_barrier) {
   if (threadIdx.x == 0) {
+    if (loop_barrier) loop_barrier[0] = 0u;   // arrival counter of k_register_loop's grid barriers
     const int tiles_ready = use_prev ? st->tiles_ready : 0;   // tiles outlive a registration of the same clouds
     for (int i = 0; i < 16; ++i) {
       const double id = (i % 5 == 0) ? 1.0 : 0.0;
@@ -827,7 +828,8 @@ int plo_launch_init_state(plo_ctx* c, const double* T0_host_or_null) {
     PLO_CUDA(c, cudaMemcpyAsync(c->scratch.p, T0_host_or_null, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
     dT0 = c->scratch.as<double>();
   }
-  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0, c->prev_valid ? 1 : 0, c->tune_force_warm ? 1 : 0);
+  PLO_CUDA(c, c->loop_barrier.reserve(sizeof(unsigned) * 2));
+  k_init_state<<<1, 32, 0, c->stream>>>(c->state.as<DevState>(), dT0, c->prev_valid ? 1 : 0, c->tune_force_warm ? 1 : 0, c->loop_barrier.as<unsigned>());
   c->launches++;
   PLO_CUDA(c, cudaGetLastError());
   return PLO_OK;
