@@ -268,6 +268,33 @@ def test_normal_equations_and_solve(oracle_mod):
     assert np.array_equal(delta, delta_b)
 
 
+def test_solve_failed_status_when_every_row_is_zero():
+    """All target normals zero: every pair is kept (finite normal, IMLS height 0) but its row of A is zero, so the
+    6x6 system has no pivot.  The reference's WeightedLS would hand a zero / NaN step to its remaining iterations
+    (src/laser_odometry.cpp:611-616 only breaks on `false`); the resident loop ends at once with PLO_REG_SOLVE_FAILED
+    and the pose it started from -- on the loop kernel, the graph form and the enqueue-all form alike."""
+    rng = np.random.default_rng(31)
+    tgt = np.zeros((4000, 12), np.float32)
+    tgt[:, 0:3] = rng.uniform(-3, 3, size=(4000, 3)) * [1, 1, 0.02]
+    src = tgt[:600].copy()
+    src[:, 0:3] += np.float32(0.01)
+    src[:, 6] = 1
+    for knobs in ({}, {"loop_kernel": 0}, {"no_graph": 1}):
+        ctx = plo.Context(0)
+        for k, v in knobs.items():
+            ctx.set_tuning(k, v)
+        ctx.set_target(tgt)
+        ctx.set_source(src)
+        st = ctx.project(np.eye(4))
+        assert st["n_pairs"] >= 100
+        delta, rank = ctx.solve_wls()
+        assert rank == 0 and np.array_equal(delta, np.eye(4))
+        T, rs = ctx.register()
+        assert rs["status"] == 4 and rs["status_name"] == "SOLVE_FAILED" and rs["iters"] == 0, (knobs, rs)
+        assert np.array_equal(T, np.eye(4))
+        ctx.close()
+
+
 def test_rank_deficient_plane(oracle_mod):
     rng = np.random.default_rng(13)
     tgt = np.zeros((5000, 12), np.float32)
