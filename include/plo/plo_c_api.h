@@ -353,22 +353,27 @@ PLO_API int64_t plo_launch_count(const plo_ctx* ctx);
 /* device milliseconds of the last index build / last registration loop, measured with
  * CUDA events on the context's stream (0 if not measured yet) */
 PLO_API int plo_last_timings(plo_ctx* ctx, float* ms_index_build, float* ms_register);
-/* per-kernel CUDA-event timing inside plo_register (off by default): when enabled every
- * projection-kernel launch of the resident loop is bracketed by an event pair on the
- * context's stream.  plo_last_kernel_timings returns the mean device ms of the launches
- * that did work in the last plo_register and how many those were. */
-/* tuning / test knobs (no reference counterpart): "chunk" (consecutive source points per warp in k_project_cold, 0 =
- * device-side policy; PLO_CHUNK in the environment at plo_create), "no_graph" (enqueue every iteration instead of the
- * conditional CUDA graph: ncu cannot profile kernel nodes of such graphs; PLO_NO_GRAPH), "force_warm" (stepped
- * projections start in the settled regime: candidate tiles are written and k_project_settled consumes them -- lets the
- * parity tests exercise that kernel through plo_project). */
+/* tuning / test knobs (no reference counterpart), also read from the environment once, at plo_create:
+ *   "chunk"        consecutive source points a warp takes per tree-walk chunk (0 = device-side policy; PLO_CHUNK)
+ *   "group"        queries per warp and round on the candidate-tile path (<= 32; 0 = sized from the cloud)
+ *   "no_graph"     enqueue every iteration instead of the loop kernel / conditional CUDA graph (ncu cannot profile
+ *                  kernel nodes of such graphs; PLO_NO_GRAPH)
+ *   "loop_kernel"  0: the weighted-LS loop as a CUDA graph of k_project + k_reduce_solve launches instead of ONE
+ *                  k_register_loop launch (PLO_LOOP_KERNEL); "fuse" 0: stand-alone reduce / solve kernels (PLO_FUSE)
+ *   "force_warm"   stepped projections start in the settled regime: candidate tiles are written and consumed -- lets
+ *                  the parity tests exercise the tile path through plo_project
+ * All forms give bitwise the same poses.  PLO_NO_CHAIN=1 in the environment: ordinary stream launches in the index
+ * build instead of programmatically dependent ones. */
 PLO_API int plo_set_tuning(plo_ctx* ctx, const char* name, int32_t value);
+/* per-kernel CUDA-event timing inside plo_register (off by default): when enabled every projection launch of the loop
+ * (enqueue-all form) is bracketed by an event pair on the context's stream.  plo_last_kernel_timings returns the mean
+ * device ms of the launches that did work in the last plo_register and how many those were. */
 PLO_API int plo_set_profiling(plo_ctx* ctx, int32_t enabled);
 PLO_API int plo_last_kernel_timings(plo_ctx* ctx, float* ms_project_mean, int32_t* n_project);
 /* the same launches one by one (ICP iteration i of the last plo_register -> ms_each[i], at most cap
  * and at most 64 entries): shows how the projection gets cheaper as the pose settles */
 PLO_API int plo_last_project_times(plo_ctx* ctx, float* ms_each, int32_t cap, int32_t* n_project);
-/* per projection of the last plo_register: how many queries k_project_settled could not answer from their candidate
+/* per projection of the last plo_register: how many queries the tile path could not answer from their candidate
  * tile and handed to the tree walk (-1: the settled kernel did not run in that projection) */
 PLO_API int plo_last_tile_misses(plo_ctx* ctx, int32_t* misses, int32_t cap, int32_t* n_project);
 /* debug builds (-DPLO_LOOP_TIMING) only: phase-boundary timestamps of the resident loop kernel */

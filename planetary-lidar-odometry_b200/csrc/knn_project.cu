@@ -3,9 +3,10 @@
 // (src/imls_icp.cpp:496-745) with ImplicitMLSFunction (:301-483) fused in,
 // and the per-map-point PCA normal pass (ComputeNormal, :753-794, call sites :411-433,:647-669).
 //
-// Two projection kernels share one per-query tail (gates, IMLS sum, output):
+// One projection (project_phase: the body of k_project, and of every iteration of k_register_loop) has two paths that
+// share one per-query tail (gates, IMLS sum, output):
 //
-// k_project_cold — one warp per query, warp-uniform control flow over the curve-sorted wide BVH of
+// the tree walk (cold_query) — one warp per query, warp-uniform control flow over the curve-sorted wide BVH of
 // index_build.cu (32 children per node, 32 points per leaf: every node test is one coalesced float4 pair
 // per lane, every leaf one coalesced 512-byte load).  Exact k-NN in three phases (knn_search.cuh):
 //   A  bound: an upper bound D of the k-th neighbour distance (squared).  Triangle inequality
@@ -31,16 +32,17 @@
 // Once the pose is settling (small last step) the walk also leaves a candidate TILE per query behind
 // (knn_search.cuh: 64 candidate points, x_ref, the radius e2 it is complete for).
 //
-// k_project_settled — the streaming kernel of the settled iterations: a warp takes a GROUP of 32 consecutive
+// the tile path (tile_query) — the streaming form of the settled iterations: a warp takes a GROUP of up to 32 consecutive
 // queries; lane = query for the per-query scalars (transform, temporal bound, tile validity
 // sqrt(D) + |x - x_ref| <= sqrt(e2)), then warp = query for each valid one: the tile arrives with two coalesced
 // 512-byte loads (evict-first: 135 MB per projection stream through, the map stays in L2), is filtered by the same
 // lower-bound test as a leaf, exact fp64 distances and ranks decide as in phase C — no tree, no dependent loads.
-// Queries whose tile does not cover the bound go to a miss list that k_project_cold (launched right behind it)
-// works off; every per-query result is bitwise the same whichever kernel produced it.
+// Queries whose tile does not cover the bound go to a self-flagging miss list that warps out of groups work off through
+// the tree walk while the others still stream tiles; every per-query result is bitwise the same whichever path produced it.
 //
-// The normal equations of the pairs are reduced and solved by k_reduce_solve (p2plane_solve.cu), one launch behind
-// the projection.  (An in-kernel variant -- per-group partial sums handed from warp to warp with release tickets, the
+// The normal equations of the pairs are reduced and solved behind a grid barrier inside k_register_loop, or by
+// k_reduce_solve (p2plane_solve.cu), one launch behind k_project, in the graph / enqueue-all forms of the loop.  (A variant
+// fused into the projection itself -- per-group partial sums handed from warp to warp with release tickets, the
 // last block solving -- was built and measured: every device-scope fence stalls the whole SM's memory pipe, 17 k of
 // them per projection cost 0.1 ms, more than the launch they save.)
 //
@@ -48,8 +50,8 @@
 // only if the list is full of coincident points is a second (k=1) search needed.
 //
 // Algorithmic bytes per source point per iteration: 24 B query + k * 24 B
-// neighbours (+ 24 B pair written) = 504 / 528 B at k = 20.  Roofline: HBM (cold kernel: in practice
-// L2, a 1 M-point map is 32 MB and stays L2-resident; settled kernel: the tiles stream from HBM).
+// neighbours (+ 24 B pair written) = 504 / 528 B at k = 20.  Roofline: HBM (tree walk: in practice
+// L2, a 1 M-point map is 32 MB and stays L2-resident; tile path: the tiles stream from HBM).
 #include <float.h>
 #include <math_constants.h>
 

@@ -388,7 +388,7 @@ __device__ __forceinline__ int filter_buffer(WarpScratch& ws, int count, float t
   return kept;
 }
 
-// ---- per-query candidate tiles (written here, consumed by k_project_settled in knn_project.cu) -----------
+// ---- per-query candidate tiles (written here, consumed by tile_query in knn_project.cu) -----------
 //
 // ICP re-projects the SAME source against the SAME map several times and once the pose settles a query moves by
 // millimetres.  A walk can therefore leave behind, per query, a TILE: up to kTileSlots candidate points (coordinates

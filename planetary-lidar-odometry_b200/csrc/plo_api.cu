@@ -898,7 +898,7 @@ static void destroy_loop_graph(plo_ctx* c) {
   c->loop_sig.clear();
 }
 
-// WHILE conditional node whose body is one ICP iteration: k_project_settled + the two k_project_cold instantiations,
+// WHILE conditional node whose body is one ICP iteration: k_project,
 // then k_reduce_solve, whose last block solves and sets the condition from the device-side state (weighted LS); for
 // the other solvers the stand-alone reduce / solve kernels of p2plane_solve.cu follow and the last of them sets it.
 static int build_loop_graph(plo_ctx* c) {

@@ -71,7 +71,7 @@ struct DevState {
   int use_prev;   // q_x / q_kd2 hold a previous projection of the same clouds (temporal bound usable)
   int chunk;      // consecutive source points per warp in the next projection (carry bound vs. balance)
   int warm;       // the last pose step was small: the next projection's queries barely move (short chunks, tiles are left behind)
-  int miss_hist[32];   // per projection of this registration: queries k_project_settled handed to the tree (-1: it did not run)
+  int miss_hist[32];   // per projection of this registration: queries the tile path handed to the tree (-1: it did not run)
   int tiles_ready; // every query has a candidate tile (or an invalid mark) from a projection of the same clouds: k_project_settled runs
 };
 
@@ -190,7 +190,7 @@ struct plo_ctx {
   int body_launches = 2;   // kernels per loop iteration of the captured body
   // tuning knobs: environment read once at plo_create (PLO_CHUNK, PLO_NO_GRAPH), or plo_set_tuning
   int tune_group = 0;        // > 0: queries per warp and fetch on the settled path (power of two <= 32)
-  int tune_chunk = -1;       // >= 0: chunk length of k_project_cold (0 = device-side policy)
+  int tune_chunk = -1;       // >= 0: chunk length of the tree walk (0 = device-side policy)
   bool tune_no_graph = false;   // enqueue-all loop instead of the conditional graph (ncu cannot profile kernel nodes of such graphs)
   bool tune_loop_kernel = true; // resident weighted-LS loop as ONE cooperative launch (k_register_loop); PLO_LOOP_KERNEL=0: graph of launches
   bool tune_fuse = true;        // resident weighted-LS loop: reduce + solve + loop tail in one launch (PLO_FUSE=0: the two stand-alone kernels)

@@ -1136,7 +1136,7 @@ def test_imls_function_and_compute_normal_entry_points(oracle_mod):
 
 
 def test_settled_kernel_parity_from_candidate_tiles(oracle_mod):
-    """k_project_settled (the streaming kernel of the settled iterations) is held to the same bars as the tree walk:
+    """The candidate-tile path (tile_query, the streaming form of the settled iterations) is held to the same bars as the tree walk:
     with the `force_warm` knob a stepped projection leaves candidate tiles behind and the next ones consume them.
     Small moves (tile hits), a move too large for most tiles (misses go to the tree through the miss list), a map of
     quantised points (ties at the bound, ties by index), coincident points (second search of the 1-NN rule), k = 32,
