@@ -330,7 +330,7 @@ __device__ __noinline__ void solve_from_sums(const double* s_sum, DevState* __re
 
 // ---- block-level reduction of the normal equations, shared by k_reduce_solve and k_register_loop ------------------
 // Pairs are taken in rounds of gridDim.x * blockDim.x (pair i of a round belongs to global thread i); per round every
-// value is summed over the warp by a fixed shuffle tree, rounds accumulate in order in lane 0, the warps of the block
+// value is summed over the warp by a fixed shuffle tree, rounds accumulate in order (one lane per value), the warps of the block
 // are summed in order: the result depends on the launch geometry only.  The pairs were written by other SMs during the
 // same launch (k_register_loop): L2 loads.  s_red: [WARPS][PLO_NSUM] shared scratch.  Writes partial[0..PLO_NSUM).
 __device__ __forceinline__ double warp_tree_sum(double v) {
@@ -339,12 +339,33 @@ __device__ __forceinline__ double warp_tree_sum(double v) {
   return v;
 }
 
+// The butterfly sums of SIXTEEN values at once: the same operand pairs as warp_tree_sum (xor 16, 8, 4, 2, 1), hence bitwise
+// the same totals, but after each exchange a lane keeps only half of the values it held -- 8 + 4 + 2 + 1 + 1 exchanges
+// instead of 16 x 5.  On return lane l holds the total of value warp_tree_slot16(l) (lanes l and l ^ 1 the same one).
+__device__ __forceinline__ int warp_tree_slot16(int lane) {
+  return (((lane >> 4) & 1) << 3) | (((lane >> 3) & 1) << 2) | (((lane >> 2) & 1) << 1) | ((lane >> 1) & 1);
+}
+__device__ __forceinline__ double warp_tree_sum16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int width = 8; width >= 1; width >>= 1) {
+    const bool up = (lane & (2 * width)) != 0;   // xor distance 2 * width: the upper partner keeps the upper half
+#pragma unroll
+    for (int i = 0; i < width; ++i) {
+      const double send = up ? v[i] : v[i + width];
+      const double keep = up ? v[i + width] : v[i];
+      v[i] = keep + __shfl_xor_sync(PLO_FULL_MASK, send, 2 * width);
+    }
+  }
+  return v[0] + __shfl_xor_sync(PLO_FULL_MASK, v[0], 1);
+}
+
 template <int WARPS>
 __device__ __forceinline__ void reduce_pairs_block(const float4* qx, const float4* qy, const float4* qn, int n_src, const DevParams& P,
                                                    double* __restrict__ partial, double (*s_red)[PLO_NSUM]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0)
     for (int t = 0; t < PLO_NSUM; ++t) s_red[warp][t] = 0.0;
+  __syncwarp();
   const int stride = (int)(gridDim.x * blockDim.x);
   const int rounds = (n_src + stride - 1) / stride;
   for (int r = 0; r < rounds; ++r) {
@@ -370,23 +391,32 @@ __device__ __forceinline__ void reduce_pairs_block(const float4* qx, const float
         }
       }
     }
-    int t = 0;
+    // 21 + 6 + 2 butterfly sums, sixteen at a time (warp_tree_sum16: the same totals as one warp_tree_sum per value);
+    // value t: 0..20 = w a_p a_q (p <= q, row-major), 21..26 = w a_p b, 27 = w, 28 = w b^2
+    const int tl = warp_tree_slot16(lane);
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
+    for (int half = 0; half < 2; ++half) {
+      double v[16];
+      int t = 0;
 #pragma unroll
-      for (int q = p; q < 6; ++q) {
-        const double v = warp_tree_sum(w * a[p] * a[q]);
-        if (lane == 0) s_red[warp][t] += v;
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = p; q < 6; ++q) {
+          if ((t >> 4) == half) v[t & 15] = w * a[p] * a[q];
+          ++t;
+        }
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        if ((t >> 4) == half) v[t & 15] = w * a[p] * b;
         ++t;
       }
-#pragma unroll
-    for (int p = 0; p < 6; ++p) {
-      const double v = warp_tree_sum(w * a[p] * b);
-      if (lane == 0) s_red[warp][21 + p] += v;
-    }
-    {
-      const double v = warp_tree_sum(w), v2 = warp_tree_sum(w * b * b);
-      if (lane == 0) { s_red[warp][27] += v; s_red[warp][28] += v2; }
+      if (half == 1) {
+        v[11] = w;           // t = 27
+        v[12] = w * b * b;   // t = 28
+        v[13] = 0.0; v[14] = 0.0; v[15] = 0.0;
+      }
+      const double tot = warp_tree_sum16(v, lane);
+      if (!(lane & 1) && half * 16 + tl < 29) s_red[warp][half * 16 + tl] += tot;
     }
 #pragma unroll
     for (int sd = 0; sd <= 6; ++sd) {   // pair count and the six drop counters
