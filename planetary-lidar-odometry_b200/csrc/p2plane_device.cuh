@@ -433,34 +433,33 @@ __device__ __forceinline__ void reduce_pairs_block(const float4* qx, const float
   }
 }
 
-// block partials -> s_sum[PLO_NSUM].  Warp w takes the partials w, w + #warps, ... (lane = value index: one coalesced
-// 288-byte row per partial, all of a thread's loads in flight together -- a sequential sum over 296 L2 round trips took
-// 16 us), adds them in that order, then thread t adds the warps' sums in order.  Every block that runs this on the same
-// partials gets the same bits.  s_stage: [#warps][PLO_NSUM] shared scratch (may alias s_sum's neighbourhood, not s_sum).
+// block partials -> s_sum[PLO_NSUM].  The block splits into groups of PLO_NSUM threads (thread t of a group = value t: one
+// coalesced 288-byte row per partial); group g takes the partials g, g + #groups, ... with up to twelve loads of a thread in
+// flight together (two L2 round trips for 296 partials and 512 threads -- a sequential sum over 296 round trips took 16 us,
+// a lane-per-value layout with its second, 4-lane pass six round trips = 3 us), adds them in that order, then thread t
+// adds the groups' sums in order.  Every block that runs this on the same partials gets the same bits.
+// s_stage: [>= blockDim / PLO_NSUM][PLO_NSUM] shared scratch (may alias s_sum's neighbourhood, not s_sum).
 __device__ __forceinline__ void sum_block_partials(const double* partials, int n_partials, double* s_sum, double (*s_stage)[PLO_NSUM]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int groups = (int)blockDim.x / PLO_NSUM;
+  const int g = (int)threadIdx.x / PLO_NSUM, t = (int)threadIdx.x % PLO_NSUM;
+  if (g < groups) {
+    double acc = 0.0;
+    for (int b0 = g; b0 < n_partials; b0 += 12 * groups) {
+      double v[12];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int t = half * 32 + lane;
-    if (t < PLO_NSUM) {
-      double acc = 0.0;
-      for (int b0 = warp; b0 < n_partials; b0 += 8 * nwarps) {   // eight loads in flight, added in order
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int b = b0 + j * nwarps;
-          v[j] = (b < n_partials) ? __ldcg(&partials[(size_t)b * PLO_NSUM + t]) : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc += v[j];
+      for (int j = 0; j < 12; ++j) {
+        const int b = b0 + j * groups;
+        v[j] = (b < n_partials) ? __ldcg(&partials[(size_t)b * PLO_NSUM + t]) : 0.0;
       }
-      s_stage[warp][t] = acc;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) acc += v[j];
     }
+    s_stage[g][t] = acc;
   }
   __syncthreads();
   if (threadIdx.x < PLO_NSUM) {
     double acc = 0.0;
-    for (int w = 0; w < nwarps; ++w) acc += s_stage[w][threadIdx.x];
+    for (int gg = 0; gg < groups; ++gg) acc += s_stage[gg][threadIdx.x];
     s_sum[threadIdx.x] = acc;
   }
   __syncthreads();
