@@ -114,6 +114,38 @@ def test_ransac_final_ls_uses_its_own_threshold():
     assert plo.config.params_from_config(cfg).ls_threshold == 0.1
 
 
+def test_transposed_butterfly_gives_the_bits_of_one_tree_per_value():
+    """csrc/p2plane_device.cuh:warp_tree_sum16 sums sixteen values over the 32 lanes with 8 + 4 + 2 + 1 + 1 exchanges; the
+    claim the bitwise reproducibility of the loop rests on is that every total has the bits of the plain xor butterfly
+    (offsets 16, 8, 4, 2, 1) of that value alone.  Lane-by-lane restatement of both in numpy, same fp64 additions."""
+    rng = np.random.default_rng(7)
+    v = rng.normal(size=(32, 16)) * np.exp(rng.uniform(-30, 30, size=(32, 16)))     # [lane][value], wide dynamic range
+    # plain butterfly: every lane ends with the total of every value
+    plain = v.copy()
+    for o in (16, 8, 4, 2, 1):
+        plain = plain + plain[np.arange(32) ^ o]
+    assert all(np.array_equal(plain[0], plain[l]) for l in range(32))
+    # transposed: after the exchange at distance 2 * width a lane keeps `width` values
+    cur = [list(v[l]) for l in range(32)]
+    for width in (8, 4, 2, 1):
+        nxt = []
+        for l in range(32):
+            up = (l & (2 * width)) != 0
+            partner = cur[l ^ (2 * width)]
+            p_up = ((l ^ (2 * width)) & (2 * width)) != 0
+            row = []
+            for i in range(width):
+                keep = cur[l][i + width] if up else cur[l][i]
+                recv = partner[i] if p_up else partner[i + width]       # what the partner sends: the half it does not keep
+                row.append(np.float64(keep) + np.float64(recv))
+            nxt.append(row)
+        cur = nxt
+    tot = [np.float64(cur[l][0]) + np.float64(cur[l ^ 1][0]) for l in range(32)]
+    for l in range(32):
+        slot = (((l >> 4) & 1) << 3) | (((l >> 3) & 1) << 2) | (((l >> 2) & 1) << 1) | ((l >> 1) & 1)
+        assert tot[l] == plain[0][slot] and np.float64(tot[l]).tobytes() == np.float64(plain[0][slot]).tobytes(), (l, slot)
+
+
 def test_tum_pose_format(tmp_path):
     T = plo.synth.scenes.pose_matrix([1.5, -2.25, 0.125], yaw_deg=90)
     f = tmp_path / "poses.txt"
