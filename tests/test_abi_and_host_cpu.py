@@ -146,6 +146,64 @@ def test_transposed_butterfly_gives_the_bits_of_one_tree_per_value():
         assert tot[l] == plain[0][slot] and np.float64(tot[l]).tobytes() == np.float64(plain[0][slot]).tobytes(), (l, slot)
 
 
+def _ldlt6_restatement(H, g, count):
+    """csrc/p2plane_device.cuh:solve_ldlt6_warp, element by element: the 6 x 7 augmented matrix, diagonal pivoting with
+    the squared ColPivHouseholderQR threshold, M[i][j] -= (M[p][hi] / dp) * M[p][lo] on the rows / columns not yet taken,
+    column-wise back substitution in reverse pivot order."""
+    eps = np.finfo(np.float64).eps
+    M = np.concatenate([H, g[:, None]], axis=1).astype(np.float64)
+    helper = (M.diagonal().max() * eps) * eps / max(count, 1.0)
+    done, order = set(), []
+    for k in range(6):
+        p, dp = -1, 0.0
+        for i in range(6):
+            if i not in done and (p < 0 or M[i, i] > dp):
+                p, dp = i, M[i, i]
+        if not (dp > 0.0) or dp < helper * (count - k):
+            break
+        done.add(p)
+        order.append(p)
+        N = M.copy()
+        for i in range(6):
+            for j in range(7):
+                if i in done or (j < 6 and j in done):
+                    continue
+                hi, lo = (i, 6) if j == 6 else (max(i, j), min(i, j))
+                N[i, j] = M[i, j] - (M[p, hi] / dp) * M[p, lo]
+        M = N
+        live = [i for i in range(6) if i not in done]
+        assert np.array_equal(M[np.ix_(live, live)], M[np.ix_(live, live)].T)       # exactly symmetric, as claimed
+    x, rhs = np.zeros(6), M[:, 6].copy()
+    for p in reversed(order):
+        x[p] = rhs[p] / M[p, p]
+        rhs = rhs - M[:, p] * x[p]
+    return x, len(order)
+
+
+def test_warp_solve_restatement_against_numpy():
+    """The algorithm of the device's 6 x 6 solve (pivot rule, rank decision, symmetric elimination, back substitution)
+    against numpy: full-rank normal equations to 1e-10 of the solution, a rank-3 system (points on a plane, normals all
+    e_z: only z, roll and pitch are observable) with the dropped unknowns left at zero, and the no-pivot case."""
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        A = rng.normal(size=(200, 6)) * rng.uniform(0.1, 10, size=6)
+        b = rng.normal(size=200)
+        H, g = A.T @ A, A.T @ b
+        x, rank = _ldlt6_restatement(H, g, 200.0)
+        ref = np.linalg.solve(H, g)
+        assert rank == 6 and np.abs(x - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    s = rng.uniform(-5, 5, size=(300, 3)) * [1, 1, 0]
+    n = np.tile([0.0, 0.0, 1.0], (300, 1))
+    A = np.concatenate([np.cross(s, n), n], axis=1)          # columns 2 (yaw), 3, 4 (x, y) are exactly zero
+    xt = np.array([0.01, -0.02, 0.0, 0.0, 0.0, 0.3])
+    H, g = A.T @ A, A.T @ (A @ xt)
+    x, rank = _ldlt6_restatement(H, g, 300.0)
+    assert rank == 3 == np.linalg.matrix_rank(A)
+    assert np.array_equal(x[[2, 3, 4]], np.zeros(3)) and np.abs(x - xt).max() < 1e-12
+    x, rank = _ldlt6_restatement(np.zeros((6, 6)), np.zeros(6), 300.0)
+    assert rank == 0 and not x.any()
+
+
 def test_tum_pose_format(tmp_path):
     T = plo.synth.scenes.pose_matrix([1.5, -2.25, 0.125], yaw_deg=90)
     f = tmp_path / "poses.txt"
